@@ -1,0 +1,701 @@
+// C ABI (include/chemtools_b200.h) over the CUDA kernels in kernels.cuh.
+// Host side is C++14; there is no CPU compute path in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/chemtools_b200.h"
+#include "kernels.cuh"
+#include "mechanism.hpp"
+
+using namespace ctb;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CT_CUDA(call)                                                                                  \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess)                                                                             \
+      return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? CT_ERR_NO_DEVICE : CT_ERR_CUDA, \
+                  std::string(#call) + ": " + cudaGetErrorString(e_));                                 \
+  } while (0)
+
+int require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(CT_ERR_NO_DEVICE, "no CUDA device available: chemtools_b200 has no CPU fallback");
+  }
+  return 0;
+}
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  cudaError_t alloc(size_t count) {
+    if (count == n && p) return cudaSuccess;
+    release();
+    n = count;
+    return cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+  }
+};
+
+MechDesc make_desc(const CompiledMech& C) {
+  MechDesc d{};
+  d.K = C.K; d.R = C.R; d.nf = C.n_fall; d.n3 = C.n_3b; d.KP = C.KP; d.Rgas = C.gas_constant; d.p_ref = C.p_ref;
+  const auto& o = C.off;
+  d.o_W = o.W; d.o_rW = o.rW; d.o_Tmid = o.Tmid; d.o_nasa = o.nasa; d.o_A = o.A; d.o_b = o.b; d.o_E = o.E; d.o_A0 = o.A0;
+  d.o_b0 = o.b0; d.o_E0 = o.E0; d.o_ta = o.troe_a; d.o_rt3 = o.troe_rt3; d.o_rt1 = o.troe_rt1; d.o_t2 = o.troe_t2;
+  d.o_eff_val = o.eff_val; d.o_eff_ptr = o.eff_ptr; d.o_sp_ptr = o.sp_ptr; d.o_sp_rxn = o.sp_rxn; d.o_sp_nu = o.sp_nu;
+  d.o_dn = o.dn; d.o_eff_sp = o.eff_sp; d.o_ftype = o.ftype; d.o_rev = o.rev; d.o_reac = o.reac; d.o_prod = o.prod;
+  d.blob_bytes = o.total;
+  return d;
+}
+
+struct DeviceInfo { int sms = 0; int max_smem_optin = 0; };
+int device_info(DeviceInfo& di) {
+  int dev = 0;
+  CT_CUDA(cudaGetDevice(&dev));
+  CT_CUDA(cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, dev));
+  CT_CUDA(cudaDeviceGetAttribute(&di.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  return 0;
+}
+
+}  // namespace
+
+struct ct_mech {
+  MechanismDef def;
+  CompiledMech C;
+  MechDesc desc{};
+  std::map<int, std::pair<unsigned char*, int*>> dev;  // device ordinal -> (blob, perm)
+  ~ct_mech() {
+    for (auto& kv : dev) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
+  }
+  int on_device(const unsigned char** blob, const int** perm) {
+    int d = 0;
+    CT_CUDA(cudaGetDevice(&d));
+    auto it = dev.find(d);
+    if (it == dev.end()) {
+      unsigned char* b = nullptr;
+      int* p = nullptr;
+      CT_CUDA(cudaMalloc(&b, C.blob.size()));
+      CT_CUDA(cudaMemcpy(b, C.blob.data(), C.blob.size(), cudaMemcpyHostToDevice));
+      CT_CUDA(cudaMalloc(&p, C.perm.size() * sizeof(int)));
+      CT_CUDA(cudaMemcpy(p, C.perm.data(), C.perm.size() * sizeof(int), cudaMemcpyHostToDevice));
+      it = dev.emplace(d, std::make_pair(b, p)).first;
+    }
+    *blob = it->second.first;
+    if (perm) *perm = it->second.second;
+    return 0;
+  }
+};
+
+struct ct_batch {
+  ct_mech* mech = nullptr;
+  int rt = 0, N = 0, K = 0;
+  int64_t n = 0;
+  double rtol = 1e-8, atol = 1e-14, t_stop = 1e-3;
+  int64_t mxstep = 500;
+  int max_order = 5, jac_mode = CT_JAC_ANALYTIC, ign_mode = 1;
+  double ign_value = 400.0;
+  bool have_ic = false, fresh = true, roberts = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  DevBuf<double> T0, p0, Y0, rho0, state, save, traj, tau, tcur, scratch, tab_t, tab_T, tab_p, atol_vec, tmp_in, tmp_out, tmp_w, tmp_qf, tmp_qr, tmp_t;
+  DevBuf<long long> stats;
+  DevBuf<int> status, order;
+  DevBuf<unsigned long long> counter;
+  const double *pT0 = nullptr, *pp0 = nullptr, *pY0 = nullptr;  // owned or borrowed device pointers
+  int nt = 0;
+  bool have_order = false;
+  // launch configuration
+  int wpb = 0, grid = 0;
+  size_t smem = 0;
+  double last_ms = 0.0;
+  int64_t launches = 0;
+  ~ct_batch() {
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+  }
+};
+
+namespace {
+
+int configure_launch(ct_batch* b) {
+  DeviceInfo di;
+  if (int r = device_info(di)) return r;
+  const MechDesc& d = b->mech ? b->mech->desc : MechDesc{};
+  const WarpLayout L = make_layout(b->N, d.R);
+  const size_t slab = (size_t)L.doubles * sizeof(double);
+  const size_t avail = (size_t)di.max_smem_optin;
+  if ((size_t)d.blob_bytes + slab > avail) return fail(CT_ERR_UNSUPPORTED, "mechanism too large for one SM's shared memory");
+  int w = (int)((avail - d.blob_bytes) / slab);
+  w = std::min(w, 16);
+  b->wpb = w;
+  b->smem = d.blob_bytes + (size_t)w * slab;
+  // persistent: one CTA per SM, never more warps than reactors
+  int64_t need = (b->n + w - 1) / w;
+  b->grid = (int)std::max<int64_t>(1, std::min<int64_t>(di.sms, need));
+  return 0;
+}
+
+BatchArgs make_args(ct_batch* b) {
+  BatchArgs a{};
+  a.rt = b->roberts ? RT_ROBERTS : b->rt;
+  a.N = b->N; a.jac_mode = b->jac_mode; a.max_order = b->max_order; a.ign_mode = b->ign_mode; a.fresh = b->fresh ? 1 : 0;
+  a.n_out = 0; a.n = b->n; a.mxstep = b->mxstep;
+  a.T0 = b->pT0; a.p0 = b->pp0; a.rho0 = b->rho0.p;
+  a.nt = b->nt; a.tab_t = b->tab_t.p; a.tab_T = b->tab_T.p; a.tab_p = b->tab_p.p;
+  a.rtol = b->rtol; a.atol = b->atol; a.atol_vec = b->atol_vec.n ? b->atol_vec.p : nullptr;
+  a.t_target = b->t_stop; a.t_stop = b->t_stop; a.ign_value = b->ign_value;
+  a.state = b->state.p; a.save = nullptr; a.save_stride = CT_LMAX * CT_NP + CT_SAVE_SCALARS; a.traj = nullptr;
+  a.tau = b->tau.p; a.tcur = b->tcur.p; a.stats = b->stats.p; a.status = b->status.p; a.counter = b->counter.p;
+  a.scratch = b->scratch.p; a.order = b->have_order ? b->order.p : nullptr;
+  return a;
+}
+
+template <class Kern>
+int set_smem(Kern k, size_t bytes) {
+  CT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+int ensure_runtime_buffers(ct_batch* b) {
+  if (int r = configure_launch(b)) return r;
+  const int R = b->mech ? b->mech->desc.R : 0;
+  CT_CUDA(b->scratch.alloc((size_t)b->grid * b->wpb * warp_scratch_doubles(b->N, R)));
+  CT_CUDA(b->tau.alloc(b->n)); CT_CUDA(b->tcur.alloc(b->n)); CT_CUDA(b->stats.alloc((size_t)b->n * 8));
+  CT_CUDA(b->status.alloc(b->n)); CT_CUDA(b->counter.alloc(1));
+  if (!b->ev0) { CT_CUDA(cudaEventCreate(&b->ev0)); CT_CUDA(cudaEventCreate(&b->ev1)); }
+  return 0;
+}
+
+int launch_integrate(ct_batch* b, BatchArgs& a) {
+  const unsigned char* blob = nullptr;
+  MechDesc d{};
+  if (b->mech) { if (int r = b->mech->on_device(&blob, nullptr)) return r; d = b->mech->desc; }
+  CT_CUDA(cudaMemsetAsync(b->counter.p, 0, sizeof(unsigned long long), b->stream));
+  CT_CUDA(cudaEventRecord(b->ev0, b->stream));
+  if (b->wpb <= 8) {
+    if (int r = set_smem(k_integrate<256>, b->smem)) return r;
+    k_integrate<256><<<b->grid, b->wpb * 32, b->smem, b->stream>>>(d, blob, a);
+  } else {
+    if (int r = set_smem(k_integrate<512>, b->smem)) return r;
+    k_integrate<512><<<b->grid, b->wpb * 32, b->smem, b->stream>>>(d, blob, a);
+  }
+  CT_CUDA(cudaGetLastError());
+  CT_CUDA(cudaEventRecord(b->ev1, b->stream));
+  CT_CUDA(cudaStreamSynchronize(b->stream));
+  float ms = 0.f;
+  CT_CUDA(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+  b->last_ms = ms;
+  b->launches += 1;
+  return 0;
+}
+
+int summarize_status(ct_batch* b, int* out) {
+  std::vector<int> st(b->n);
+  CT_CUDA(cudaMemcpy(st.data(), b->status.p, b->n * sizeof(int), cudaMemcpyDeviceToHost));
+  int worst = 0;
+  bool all_tstop = true, any_live = false;
+  for (int s : st) {
+    if (s < worst) worst = s;
+    if (s != CT_TSTOP_RETURN) all_tstop = false;
+    any_live = true;
+  }
+  *out = worst < 0 ? worst : (all_tstop && any_live ? CT_TSTOP_RETURN : CT_SUCCESS);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ct_last_error(void) { return g_err.c_str(); }
+const char* ct_version(void) { return "chemtools_b200 0.1 (sm_100a)"; }
+
+ct_mech* ct_mech_load(const char* path, const char* phase_id, int* status) { return ct_mech_load_ex(path, phase_id, nullptr, status); }
+
+ct_mech* ct_mech_load_ex(const char* path, const char* phase_id, const char* constants, int* status) {
+  auto set = [&](int s) { if (status) *status = s; };
+  if (!path) { set(fail(CT_ERR_INVALID, "null mechanism path")); return nullptr; }
+  try {
+    std::unique_ptr<ct_mech> m(new ct_mech);
+    const std::string p(path);
+    const bool is_ctm = p.size() > 4 && p.compare(p.size() - 4, 4, ".ctm") == 0;
+    m->def = is_ctm ? read_ctm(p) : parse_cti(p, phase_id);
+    m->C = compile_mechanism(m->def, constants ? constants : "");
+    m->desc = make_desc(m->C);
+    if (m->C.K + 1 > CT_NP) { set(fail(CT_ERR_UNSUPPORTED, "more than 63 species: the warp-per-reactor kernels hold 2 state components per lane")); return nullptr; }
+    if (m->C.n_fall + m->C.n_3b > CT_NP) { set(fail(CT_ERR_UNSUPPORTED, "more than 64 third-body/falloff reactions")); return nullptr; }
+    set(0);
+    return m.release();
+  } catch (const std::exception& e) {
+    set(fail(CT_ERR_MECH, e.what()));
+    return nullptr;
+  }
+}
+void ct_mech_destroy(ct_mech* m) { delete m; }
+int ct_mech_save_ctm(const ct_mech* m, const char* path) {
+  if (!m || !path) return fail(CT_ERR_INVALID, "null argument");
+  try { write_ctm(m->def, path); } catch (const std::exception& e) { return fail(CT_ERR_MECH, e.what()); }
+  return 0;
+}
+int ct_mech_n_species(const ct_mech* m) { return m ? m->C.K : fail(CT_ERR_INVALID, "null mech"); }
+int ct_mech_n_reactions(const ct_mech* m) { return m ? m->C.R : fail(CT_ERR_INVALID, "null mech"); }
+int ct_mech_n_elements(const ct_mech* m) { return m ? (int)m->C.elements.size() : fail(CT_ERR_INVALID, "null mech"); }
+int ct_mech_species_index(const ct_mech* m, const char* name) {
+  if (!m || !name) return -1;
+  for (int k = 0; k < m->C.K; ++k) if (m->C.species_names[k] == name) return k;
+  return -1;
+}
+const char* ct_mech_species_name(const ct_mech* m, int k) { return (m && k >= 0 && k < m->C.K) ? m->C.species_names[k].c_str() : nullptr; }
+const char* ct_mech_reaction_equation(const ct_mech* m, int i) { return (m && i >= 0 && i < m->C.R) ? m->C.equations[i].c_str() : nullptr; }
+const char* ct_mech_element_name(const ct_mech* m, int e) { return (m && e >= 0 && e < (int)m->C.elements.size()) ? m->C.elements[e].c_str() : nullptr; }
+double ct_mech_n_atoms(const ct_mech* m, int k, int e) {
+  if (!m || k < 0 || k >= m->C.K || e < 0 || e >= (int)m->C.elements.size()) return 0.0;
+  return m->C.natoms[(size_t)k * m->C.elements.size() + e];
+}
+int ct_mech_molecular_weights(const ct_mech* m, double* W) {
+  if (!m || !W) return fail(CT_ERR_INVALID, "null argument");
+  std::copy(m->C.W.begin(), m->C.W.end(), W);
+  return 0;
+}
+double ct_mech_gas_constant(const ct_mech* m) { return m ? m->C.gas_constant : 0.0; }
+int ct_mech_compiled_arrays(const ct_mech* m, int* perm, double* A, double* b, double* EaR) {
+  if (!m) return fail(CT_ERR_INVALID, "null mech");
+  const auto& C = m->C;
+  const unsigned char* base = C.blob.data();
+  if (perm) std::copy(C.perm.begin(), C.perm.end(), perm);
+  if (A) std::memcpy(A, base + C.off.A, C.R * sizeof(double));
+  if (b) std::memcpy(b, base + C.off.b, C.R * sizeof(double));
+  if (EaR) std::memcpy(EaR, base + C.off.E, C.R * sizeof(double));
+  return 0;
+}
+int ct_mech_mole_to_mass(const ct_mech* m, int64_t n, const double* X, double* Y) {
+  if (!m || !X || !Y || n < 0) return fail(CT_ERR_INVALID, "bad argument");
+  const int K = m->C.K;
+  for (int64_t i = 0; i < n; ++i) {
+    double s = 0.0;
+    for (int k = 0; k < K; ++k) s += X[i * K + k] * m->C.W[k];
+    if (!(s > 0.0)) return fail(CT_ERR_INVALID, "composition sums to zero");
+    for (int k = 0; k < K; ++k) Y[i * K + k] = X[i * K + k] * m->C.W[k] / s;
+  }
+  return 0;
+}
+int ct_mech_flop_model(const ct_mech* m, int reactor_type, double out[4]) {
+  if (!m || !out) return fail(CT_ERR_INVALID, "null argument");
+  const int N = reactor_type <= CT_CONST_VOL ? m->C.K + 1 : m->C.K;
+  out[0] = m->C.flops_rhs; out[1] = m->C.flops_jac;
+  out[2] = 2.0 / 3.0 * (double)N * N * N; out[3] = 2.0 * (double)N * N;
+  return 0;
+}
+
+int ct_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+int ct_set_device(int ordinal) { if (int r = require_device()) return r; CT_CUDA(cudaSetDevice(ordinal)); return 0; }
+
+ct_batch* ct_batch_create(ct_mech* m, int rt, int64_t n, int* status) {
+  auto set = [&](int s) { if (status) *status = s; };
+  if (!m || n < 0 || rt < 0 || rt > CT_TABLE_TP) { set(fail(CT_ERR_INVALID, "bad batch arguments")); return nullptr; }
+  if (int r = require_device()) { set(r); return nullptr; }
+  ct_batch* b = new ct_batch;
+  b->mech = m; b->rt = rt; b->n = n; b->K = m->C.K; b->N = rt <= CT_CONST_VOL ? m->C.K + 1 : m->C.K;
+  set(0);
+  return b;
+}
+void ct_batch_destroy(ct_batch* b) { delete b; }
+int ct_batch_n_state(const ct_batch* b) { return b ? b->N : fail(CT_ERR_INVALID, "null batch"); }
+int ct_batch_set_stream(ct_batch* b, void* s) { if (!b) return fail(CT_ERR_INVALID, "null batch"); b->stream = (cudaStream_t)s; return 0; }
+
+static int finish_ic(ct_batch* b) {
+  const unsigned char* blob = nullptr;
+  if (int r = b->mech->on_device(&blob, nullptr)) return r;
+  CT_CUDA(b->rho0.alloc(b->n));
+  CT_CUDA(b->state.alloc((size_t)b->n * b->N));
+  if (b->n > 0) {
+    const int threads = 128;
+    const int blocks = (int)std::min<int64_t>((b->n + threads - 1) / threads, 4096);
+    k_init<<<blocks, threads, 0, b->stream>>>(b->mech->desc, blob, b->rt, b->n, b->pT0, b->pp0, b->pY0, b->state.p, b->rho0.p, b->N);
+    CT_CUDA(cudaGetLastError());
+  }
+  b->have_ic = true; b->fresh = true;
+  return 0;
+}
+int ct_batch_set_ic(ct_batch* b, const double* T, const double* p, const double* Y) {
+  if (!b || !T || !p || !Y) return fail(CT_ERR_INVALID, "null argument");
+  CT_CUDA(b->T0.alloc(b->n)); CT_CUDA(b->p0.alloc(b->n)); CT_CUDA(b->Y0.alloc((size_t)b->n * b->K));
+  CT_CUDA(cudaMemcpyAsync(b->T0.p, T, b->n * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+  CT_CUDA(cudaMemcpyAsync(b->p0.p, p, b->n * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+  CT_CUDA(cudaMemcpyAsync(b->Y0.p, Y, (size_t)b->n * b->K * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+  b->pT0 = b->T0.p; b->pp0 = b->p0.p; b->pY0 = b->Y0.p;
+  return finish_ic(b);
+}
+int ct_batch_set_ic_device(ct_batch* b, const double* dT, const double* dp, const double* dY) {
+  if (!b || !dT || !dp || !dY) return fail(CT_ERR_INVALID, "null argument");
+  b->pT0 = dT; b->pp0 = dp; b->pY0 = dY;
+  return finish_ic(b);
+}
+int ct_batch_set_tolerances(ct_batch* b, double rtol, double atol) {
+  if (!b) return fail(CT_ERR_INVALID, "null batch");
+  // same validation as IStrategy::Initialise (interface.cpp:300-317): negative tolerances are illegal
+  if (!(rtol >= 0.0) || !(atol >= 0.0) || (rtol == 0.0 && atol == 0.0)) return fail(CT_ILL_INPUT, "tolerances must be non-negative and not both zero");
+  b->rtol = rtol; b->atol = atol;
+  return 0;
+}
+int ct_batch_set_stop_time(ct_batch* b, double t_end) {
+  if (!b) return fail(CT_ERR_INVALID, "null batch");
+  if (!(t_end > 0.0)) return fail(CT_ILL_INPUT, "stop time must be positive");
+  b->t_stop = t_end;
+  return 0;
+}
+int ct_batch_set_max_steps(ct_batch* b, int64_t mx) { if (!b) return fail(CT_ERR_INVALID, "null batch"); b->mxstep = mx > 0 ? mx : 500; return 0; }
+int ct_batch_set_max_order(ct_batch* b, int q) {
+  if (!b) return fail(CT_ERR_INVALID, "null batch");
+  if (q < 1 || q > 5) return fail(CT_ILL_INPUT, "BDF order must be in 1..5");
+  b->max_order = q;
+  return 0;
+}
+int ct_batch_set_jacobian(ct_batch* b, int mode) {
+  if (!b || (mode != CT_JAC_DQ && mode != CT_JAC_ANALYTIC)) return fail(CT_ERR_INVALID, "bad Jacobian mode");
+  b->jac_mode = mode;
+  return 0;
+}
+int ct_batch_set_ignition(ct_batch* b, int mode, double value) {
+  if (!b || (mode != 0 && mode != 1)) return fail(CT_ERR_INVALID, "bad ignition mode");
+  b->ign_mode = mode; b->ign_value = value;
+  return 0;
+}
+int ct_batch_set_tp_table(ct_batch* b, int nt, const double* t, const double* T, const double* p) {
+  if (!b || nt < 2 || !t || !T || !p) return fail(CT_ERR_INVALID, "bad table arguments");
+  if (b->rt != CT_TABLE_TP) return fail(CT_ERR_INVALID, "T-p table on a reactor type other than CT_TABLE_TP");
+  for (int i = 1; i < nt; ++i) if (!(t[i] > t[i - 1])) return fail(CT_ILL_INPUT, "table times must increase strictly");
+  CT_CUDA(b->tab_t.alloc(nt)); CT_CUDA(b->tab_T.alloc((size_t)b->n * nt)); CT_CUDA(b->tab_p.alloc((size_t)b->n * nt));
+  CT_CUDA(cudaMemcpyAsync(b->tab_t.p, t, nt * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+  CT_CUDA(cudaMemcpyAsync(b->tab_T.p, T, (size_t)b->n * nt * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+  CT_CUDA(cudaMemcpyAsync(b->tab_p.p, p, (size_t)b->n * nt * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+  b->nt = nt;
+  return 0;
+}
+int ct_batch_set_order(ct_batch* b, const int32_t* order) {
+  if (!b) return fail(CT_ERR_INVALID, "null batch");
+  if (!order) { b->have_order = false; return 0; }
+  CT_CUDA(b->order.alloc(b->n));
+  CT_CUDA(cudaMemcpyAsync(b->order.p, order, b->n * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+  b->have_order = true;
+  return 0;
+}
+
+static int precheck_integrate(ct_batch* b) {
+  if (!b) return fail(CT_ERR_INVALID, "null batch");
+  if (!b->have_ic) return fail(CT_ILL_INPUT, "initial conditions not set");
+  if (b->rt == CT_TABLE_TP && b->nt < 2) return fail(CT_ILL_INPUT, "CT_TABLE_TP reactor without a T-p table");
+  return ensure_runtime_buffers(b);
+}
+
+int ct_batch_integrate(ct_batch* b, double t_target) {
+  if (int r = precheck_integrate(b)) return r;
+  if (b->n == 0) return CT_SUCCESS;
+  if (!(t_target > 0.0)) return fail(CT_ILL_INPUT, "t_target must be positive");
+  BatchArgs a = make_args(b);
+  a.t_target = t_target;
+  const bool resumable = t_target < b->t_stop || !b->fresh;
+  if (resumable) {
+    CT_CUDA(b->save.alloc((size_t)b->n * a.save_stride));
+    a.save = b->save.p;
+  }
+  if (b->fresh) CT_CUDA(cudaMemsetAsync(b->status.p, 0, b->n * sizeof(int), b->stream));
+  else {
+    // reactors that returned CV_SUCCESS at the previous output stay live: status back to 0 happens on device
+  }
+  if (int r = launch_integrate(b, a)) return r;
+  b->fresh = false;
+  int out = 0;
+  if (int r = summarize_status(b, &out)) return r;
+  return out;
+}
+
+int ct_batch_integrate_trajectory(ct_batch* b, int n_out, double* traj) {
+  if (int r = precheck_integrate(b)) return r;
+  if (n_out < 1 || !traj) return fail(CT_ERR_INVALID, "bad trajectory arguments");
+  if (!b->fresh) return fail(CT_ILL_INPUT, "trajectory integration needs a fresh batch (set the initial conditions again)");
+  if (b->n == 0) return CT_SUCCESS;
+  CT_CUDA(b->traj.alloc((size_t)b->n * n_out * b->N));
+  BatchArgs a = make_args(b);
+  a.n_out = n_out; a.traj = b->traj.p;
+  CT_CUDA(cudaMemsetAsync(b->status.p, 0, b->n * sizeof(int), b->stream));
+  if (int r = launch_integrate(b, a)) return r;
+  b->fresh = false;
+  CT_CUDA(cudaMemcpy(traj, b->traj.p, (size_t)b->n * n_out * b->N * sizeof(double), cudaMemcpyDeviceToHost));
+  int out = 0;
+  if (int r = summarize_status(b, &out)) return r;
+  return out;
+}
+
+int ct_batch_get_state(ct_batch* b, double* out) {
+  if (!b || !out) return fail(CT_ERR_INVALID, "null argument");
+  if (!b->have_ic) return fail(CT_ILL_INPUT, "initial conditions not set");
+  CT_CUDA(cudaMemcpyAsync(out, b->state.p, (size_t)b->n * b->N * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  CT_CUDA(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+int ct_batch_get_state_device(ct_batch* b, const double** dptr) {
+  if (!b || !dptr) return fail(CT_ERR_INVALID, "null argument");
+  *dptr = b->state.p;
+  return 0;
+}
+#define CT_GETTER(name, buf, type, mult)                                                              \
+  int name(ct_batch* b, type* out) {                                                                 \
+    if (!b || !out) return fail(CT_ERR_INVALID, "null argument");                                     \
+    if (!b->buf.p || b->launches == 0) return fail(CT_ILL_INPUT, "nothing integrated yet");           \
+    CT_CUDA(cudaMemcpyAsync(out, b->buf.p, (size_t)b->n * (mult) * sizeof(type), cudaMemcpyDeviceToHost, b->stream)); \
+    CT_CUDA(cudaStreamSynchronize(b->stream));                                                        \
+    return 0;                                                                                         \
+  }
+CT_GETTER(ct_batch_get_time, tcur, double, 1)
+CT_GETTER(ct_batch_get_ignition, tau, double, 1)
+CT_GETTER(ct_batch_get_status, status, int32_t, 1)
+int ct_batch_get_stats(ct_batch* b, int64_t* out) {
+  if (!b || !out) return fail(CT_ERR_INVALID, "null argument");
+  if (!b->stats.p || b->launches == 0) return fail(CT_ILL_INPUT, "nothing integrated yet");
+  CT_CUDA(cudaMemcpyAsync(out, b->stats.p, (size_t)b->n * 8 * sizeof(long long), cudaMemcpyDeviceToHost, b->stream));
+  CT_CUDA(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+double ct_batch_last_kernel_ms(const ct_batch* b) { return b ? b->last_ms : 0.0; }
+int64_t ct_batch_launch_count(const ct_batch* b) { return b ? b->launches : 0; }
+int ct_batch_warps_per_sm(const ct_batch* b) { return b ? b->wpb : 0; }
+
+// ---------------------------------------------------------------- stand-alone kernels
+static int standalone_cfg(ct_batch* b, int* wpb, int* grid, size_t* smem, bool need_scratch) {
+  if (int r = configure_launch(b)) return r;
+  *wpb = std::min(b->wpb, 8);
+  const WarpLayout L = make_layout(b->N, b->mech->desc.R);
+  *smem = b->mech->desc.blob_bytes + (size_t)*wpb * L.doubles * sizeof(double);
+  DeviceInfo di;
+  if (int r = device_info(di)) return r;
+  *grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)di.sms * 1, (b->n + *wpb - 1) / *wpb));
+  if (need_scratch) CT_CUDA(b->scratch.alloc(std::max<size_t>(b->scratch.n, (size_t)*grid * *wpb * warp_scratch_doubles(b->N, b->mech->desc.R))));
+  return 0;
+}
+
+int ct_rhs_eval(ct_batch* b, const double* states, const double* times, double* ydot, double* wdot, double* qf, double* qr) {
+  if (!b || !states || !ydot) return fail(CT_ERR_INVALID, "null argument");
+  if (!b->have_ic) return fail(CT_ILL_INPUT, "initial conditions not set");
+  if ((qf == nullptr) != (qr == nullptr)) return fail(CT_ERR_INVALID, "qf and qr must be given together");
+  const int R = b->mech->desc.R;
+  int wpb, grid; size_t smem;
+  if (int r = standalone_cfg(b, &wpb, &grid, &smem, false)) return r;
+  const unsigned char* blob; const int* perm;
+  if (int r = b->mech->on_device(&blob, &perm)) return r;
+  const size_t nN = (size_t)b->n * b->N;
+  CT_CUDA(b->tmp_in.alloc(nN)); CT_CUDA(b->tmp_out.alloc(nN)); CT_CUDA(b->tmp_w.alloc((size_t)b->n * b->K));
+  CT_CUDA(cudaMemcpyAsync(b->tmp_in.p, states, nN * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+  if (times) { CT_CUDA(b->tmp_t.alloc(b->n)); CT_CUDA(cudaMemcpyAsync(b->tmp_t.p, times, b->n * sizeof(double), cudaMemcpyHostToDevice, b->stream)); }
+  if (qf) { CT_CUDA(b->tmp_qf.alloc((size_t)b->n * R)); CT_CUDA(b->tmp_qr.alloc((size_t)b->n * R)); }
+  BatchArgs a = make_args(b);
+  if (int r = set_smem(k_rhs, smem)) return r;
+  k_rhs<<<grid, wpb * 32, smem, b->stream>>>(b->mech->desc, blob, a, b->tmp_in.p, times ? b->tmp_t.p : nullptr, b->tmp_out.p,
+                                             b->tmp_w.p, qf ? b->tmp_qf.p : nullptr, qf ? b->tmp_qr.p : nullptr, perm);
+  CT_CUDA(cudaGetLastError());
+  b->launches += 1;
+  CT_CUDA(cudaMemcpyAsync(ydot, b->tmp_out.p, nN * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  if (wdot) CT_CUDA(cudaMemcpyAsync(wdot, b->tmp_w.p, (size_t)b->n * b->K * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  if (qf) {
+    CT_CUDA(cudaMemcpyAsync(qf, b->tmp_qf.p, (size_t)b->n * R * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    CT_CUDA(cudaMemcpyAsync(qr, b->tmp_qr.p, (size_t)b->n * R * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  }
+  CT_CUDA(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+int ct_rhs_time(ct_batch* b, const double* states, int reps, double* ms) {
+  if (!b || !states || !ms || reps < 1) return fail(CT_ERR_INVALID, "bad argument");
+  if (!b->have_ic) return fail(CT_ILL_INPUT, "initial conditions not set");
+  int wpb, grid; size_t smem;
+  if (int r = standalone_cfg(b, &wpb, &grid, &smem, false)) return r;
+  const unsigned char* blob; const int* perm;
+  if (int r = b->mech->on_device(&blob, &perm)) return r;
+  const size_t nN = (size_t)b->n * b->N;
+  CT_CUDA(b->tmp_in.alloc(nN)); CT_CUDA(b->tmp_out.alloc(nN)); CT_CUDA(b->tmp_w.alloc((size_t)b->n * b->K));
+  CT_CUDA(cudaMemcpy(b->tmp_in.p, states, nN * sizeof(double), cudaMemcpyHostToDevice));
+  if (!b->ev0) { CT_CUDA(cudaEventCreate(&b->ev0)); CT_CUDA(cudaEventCreate(&b->ev1)); }
+  BatchArgs a = make_args(b);
+  if (int r = set_smem(k_rhs, smem)) return r;
+  for (int w = 0; w < 3; ++w) k_rhs<<<grid, wpb * 32, smem, b->stream>>>(b->mech->desc, blob, a, b->tmp_in.p, nullptr, b->tmp_out.p, b->tmp_w.p, nullptr, nullptr, perm);
+  CT_CUDA(cudaEventRecord(b->ev0, b->stream));
+  for (int w = 0; w < reps; ++w) k_rhs<<<grid, wpb * 32, smem, b->stream>>>(b->mech->desc, blob, a, b->tmp_in.p, nullptr, b->tmp_out.p, b->tmp_w.p, nullptr, nullptr, perm);
+  CT_CUDA(cudaEventRecord(b->ev1, b->stream));
+  CT_CUDA(cudaStreamSynchronize(b->stream));
+  CT_CUDA(cudaGetLastError());
+  float t = 0.f;
+  CT_CUDA(cudaEventElapsedTime(&t, b->ev0, b->ev1));
+  *ms = t / reps;
+  b->launches += reps + 3;
+  return 0;
+}
+
+static int jac_launch(ct_batch* b, int mode, const double* d_states, const double* d_times, double* d_J, int reps, double* ms) {
+  int wpb, grid; size_t smem;
+  if (int r = standalone_cfg(b, &wpb, &grid, &smem, true)) return r;
+  const unsigned char* blob;
+  if (int r = b->mech->on_device(&blob, nullptr)) return r;
+  if (!b->ev0) { CT_CUDA(cudaEventCreate(&b->ev0)); CT_CUDA(cudaEventCreate(&b->ev1)); }
+  BatchArgs a = make_args(b);
+  a.jac_mode = mode;
+  if (int r = set_smem(k_jacobian, smem)) return r;
+  if (ms) for (int w = 0; w < 2; ++w) k_jacobian<<<grid, wpb * 32, smem, b->stream>>>(b->mech->desc, blob, a, d_states, d_times, 1e-8, d_J);
+  CT_CUDA(cudaEventRecord(b->ev0, b->stream));
+  for (int w = 0; w < reps; ++w) k_jacobian<<<grid, wpb * 32, smem, b->stream>>>(b->mech->desc, blob, a, d_states, d_times, 1e-8, d_J);
+  CT_CUDA(cudaEventRecord(b->ev1, b->stream));
+  CT_CUDA(cudaStreamSynchronize(b->stream));
+  CT_CUDA(cudaGetLastError());
+  float t = 0.f;
+  CT_CUDA(cudaEventElapsedTime(&t, b->ev0, b->ev1));
+  if (ms) *ms = t / reps;
+  b->launches += reps;
+  return 0;
+}
+
+int ct_jacobian_eval(ct_batch* b, int mode, const double* states, const double* times, double* J) {
+  if (!b || !states || !J) return fail(CT_ERR_INVALID, "null argument");
+  if (!b->have_ic) return fail(CT_ILL_INPUT, "initial conditions not set");
+  const size_t nN = (size_t)b->n * b->N;
+  CT_CUDA(b->tmp_in.alloc(nN)); CT_CUDA(b->tmp_out.alloc(nN * b->N));
+  CT_CUDA(cudaMemcpy(b->tmp_in.p, states, nN * sizeof(double), cudaMemcpyHostToDevice));
+  if (times) { CT_CUDA(b->tmp_t.alloc(b->n)); CT_CUDA(cudaMemcpy(b->tmp_t.p, times, b->n * sizeof(double), cudaMemcpyHostToDevice)); }
+  if (int r = jac_launch(b, mode, b->tmp_in.p, times ? b->tmp_t.p : nullptr, b->tmp_out.p, 1, nullptr)) return r;
+  CT_CUDA(cudaMemcpy(J, b->tmp_out.p, nN * b->N * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+int ct_jacobian_time(ct_batch* b, int mode, const double* states, int reps, double* ms) {
+  if (!b || !states || !ms || reps < 1) return fail(CT_ERR_INVALID, "bad argument");
+  if (!b->have_ic) return fail(CT_ILL_INPUT, "initial conditions not set");
+  const size_t nN = (size_t)b->n * b->N;
+  CT_CUDA(b->tmp_in.alloc(nN)); CT_CUDA(b->tmp_out.alloc(nN * b->N));
+  CT_CUDA(cudaMemcpy(b->tmp_in.p, states, nN * sizeof(double), cudaMemcpyHostToDevice));
+  return jac_launch(b, mode, b->tmp_in.p, nullptr, b->tmp_out.p, reps, ms);
+}
+
+static int lu_run(int N, int64_t n, const double* dA, const double* db, double* dx, int* dinfo, int reps, int solves, double* ms) {
+  DeviceInfo di;
+  if (int r = device_info(di)) return r;
+  const WarpLayout L = make_layout(N, 4);
+  const size_t slab = (size_t)L.doubles * sizeof(double);
+  int wpb = (int)std::min<size_t>(8, (size_t)di.max_smem_optin / slab);
+  if (wpb < 1) return fail(CT_ERR_UNSUPPORTED, "matrix too large for shared memory");
+  const size_t smem = wpb * slab;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(di.sms, (n + wpb - 1) / wpb));
+  if (int r = set_smem(k_lu_solve, smem)) return r;
+  cudaEvent_t e0, e1;
+  CT_CUDA(cudaEventCreate(&e0)); CT_CUDA(cudaEventCreate(&e1));
+  if (ms) for (int w = 0; w < 2; ++w) k_lu_solve<<<grid, wpb * 32, smem>>>(N, n, dA, db, dx, dinfo, solves);
+  CT_CUDA(cudaEventRecord(e0));
+  for (int w = 0; w < reps; ++w) k_lu_solve<<<grid, wpb * 32, smem>>>(N, n, dA, db, dx, dinfo, solves);
+  CT_CUDA(cudaEventRecord(e1));
+  CT_CUDA(cudaDeviceSynchronize());
+  CT_CUDA(cudaGetLastError());
+  float t = 0.f;
+  CT_CUDA(cudaEventElapsedTime(&t, e0, e1));
+  if (ms) *ms = t / reps;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return 0;
+}
+
+int ct_lu_solve(int N, int64_t n, const double* A, const double* b, double* x, int32_t* info) {
+  if (int r = require_device()) return r;
+  if (N < 1 || N > CT_NP || n < 0 || !A || !b || !x) return fail(CT_ERR_INVALID, "bad argument");
+  DevBuf<double> dA, db, dx; DevBuf<int> dinfo;
+  CT_CUDA(dA.alloc((size_t)n * N * N)); CT_CUDA(db.alloc((size_t)n * N)); CT_CUDA(dx.alloc((size_t)n * N)); CT_CUDA(dinfo.alloc(n));
+  CT_CUDA(cudaMemcpy(dA.p, A, (size_t)n * N * N * sizeof(double), cudaMemcpyHostToDevice));
+  CT_CUDA(cudaMemcpy(db.p, b, (size_t)n * N * sizeof(double), cudaMemcpyHostToDevice));
+  CT_CUDA(cudaMemset(dx.p, 0, (size_t)n * N * sizeof(double)));
+  if (n > 0) if (int r = lu_run(N, n, dA.p, db.p, dx.p, dinfo.p, 1, 1, nullptr)) return r;
+  CT_CUDA(cudaMemcpy(x, dx.p, (size_t)n * N * sizeof(double), cudaMemcpyDeviceToHost));
+  if (info) CT_CUDA(cudaMemcpy(info, dinfo.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+int ct_lu_time(int N, int64_t n, int reps, int solves, double* ms) {
+  if (int r = require_device()) return r;
+  if (N < 1 || N > CT_NP || n < 1 || reps < 1 || !ms) return fail(CT_ERR_INVALID, "bad argument");
+  std::vector<double> A((size_t)n * N * N), b((size_t)n * N, 1.0);
+  unsigned long long s = 88172645463325252ULL;
+  for (auto& v : A) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; v = (double)(s >> 11) / 9007199254740992.0 - 0.5; }
+  for (int64_t i = 0; i < n; ++i) for (int d = 0; d < N; ++d) A[(size_t)i * N * N + d * N + d] += 4.0;
+  DevBuf<double> dA, db, dx; DevBuf<int> dinfo;
+  CT_CUDA(dA.alloc(A.size())); CT_CUDA(db.alloc(b.size())); CT_CUDA(dx.alloc(b.size())); CT_CUDA(dinfo.alloc(n));
+  CT_CUDA(cudaMemcpy(dA.p, A.data(), A.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CT_CUDA(cudaMemcpy(db.p, b.data(), b.size() * sizeof(double), cudaMemcpyHostToDevice));
+  return lu_run(N, n, dA.p, db.p, dx.p, dinfo.p, reps, solves, ms);
+}
+
+int ct_measure_fp64_peak(double* tflops) {
+  if (int r = require_device()) return r;
+  if (!tflops) return fail(CT_ERR_INVALID, "null argument");
+  DeviceInfo di;
+  if (int r = device_info(di)) return r;
+  const int blocks = di.sms * 8, threads = 256, iters = 8192;
+  DevBuf<double> out;
+  CT_CUDA(out.alloc((size_t)blocks * threads));
+  cudaEvent_t e0, e1;
+  CT_CUDA(cudaEventCreate(&e0)); CT_CUDA(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CT_CUDA(cudaEventRecord(e0));
+    k_dfma_peak<<<blocks, threads>>>(out.p, iters);
+    CT_CUDA(cudaEventRecord(e1));
+    CT_CUDA(cudaDeviceSynchronize());
+    float t = 0.f;
+    CT_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+    best = std::max(best, fl / (t * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *tflops = best;
+  return 0;
+}
+
+int ct_roberts_selftest(int n_out, const double* t_out, double rtol, const double* atol3, double* y_out, int64_t* stats8) {
+  if (int r = require_device()) return r;
+  if (n_out < 1 || !t_out || !atol3 || !y_out) return fail(CT_ERR_INVALID, "bad argument");
+  ct_batch b;
+  b.mech = nullptr; b.roberts = true; b.rt = 0; b.N = 3; b.K = 0; b.n = 1;
+  b.rtol = rtol; b.atol = 0.0; b.mxstep = 500; b.jac_mode = CT_JAC_ANALYTIC;
+  b.t_stop = 1e300;
+  CT_CUDA(b.atol_vec.alloc(3));
+  CT_CUDA(cudaMemcpy(b.atol_vec.p, atol3, 3 * sizeof(double), cudaMemcpyHostToDevice));
+  CT_CUDA(b.state.alloc(3));
+  const double y0[3] = {1.0, 0.0, 0.0};
+  CT_CUDA(cudaMemcpy(b.state.p, y0, sizeof y0, cudaMemcpyHostToDevice));
+  b.have_ic = true;
+  if (int r = ensure_runtime_buffers(&b)) return r;
+  BatchArgs a = make_args(&b);
+  DevBuf<double> d_tout;
+  CT_CUDA(d_tout.alloc(n_out));
+  CT_CUDA(cudaMemcpy(d_tout.p, t_out, n_out * sizeof(double), cudaMemcpyHostToDevice));
+  CT_CUDA(b.traj.alloc((size_t)n_out * 3));
+  CT_CUDA(cudaMemset(b.status.p, 0, sizeof(int)));
+  a.n_out = n_out; a.traj = b.traj.p; a.out_times = d_tout.p; a.T0 = nullptr; a.p0 = nullptr; a.rho0 = nullptr;
+  if (int r = launch_integrate(&b, a)) return r;
+  int st = 0;
+  CT_CUDA(cudaMemcpy(&st, b.status.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (st < 0) return fail(st, "device stepper failed on the Roberts problem");
+  CT_CUDA(cudaMemcpy(y_out, b.traj.p, (size_t)n_out * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (stats8) CT_CUDA(cudaMemcpy(stats8, b.stats.p, 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // extern "C"

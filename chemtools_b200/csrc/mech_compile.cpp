@@ -1,0 +1,209 @@
+// Mechanism compiler back end: MechanismDef (file units) -> CompiledMech
+// (Cantera's kmol-m-s-K-J system, device reaction order, one flat blob that
+// the kernels stage into shared memory).  See DESIGN.md "Mechanism blob".
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "mechanism.hpp"
+
+namespace ctb {
+
+const char* const kDefaultConstants = "cantera-2.6";
+
+const ConstantSet& constant_set(const std::string& name) {
+  // Cantera's constants changed between releases and the reference does not
+  // pin one.  "cantera-2.6": CODATA-2018 R and abridged IUPAC
+  // weights (2.5/2.6); "cantera-2.4": the older table.
+  static const ConstantSet sets[] = {
+      {"cantera-2.6", 8314.46261815324, 101325.0, 4.184, {{"H", 1.008}, {"C", 12.011}, {"N", 14.007}, {"O", 15.999}, {"Ar", 39.948}}},
+      {"cantera-2.4", 8314.4621, 101325.0, 4.184, {{"H", 1.00794}, {"C", 12.0107}, {"N", 14.0067}, {"O", 15.9994}, {"Ar", 39.948}}},
+  };
+  for (auto& s : sets) if (s.name == name) return s;
+  throw MechError("unknown constant set '" + name + "' (known: cantera-2.6, cantera-2.4)");
+}
+
+namespace {
+template <class T>
+int append(std::vector<unsigned char>& blob, const std::vector<T>& v) {
+  while (blob.size() % 16) blob.push_back(0);
+  int off = (int)blob.size();
+  const unsigned char* p = reinterpret_cast<const unsigned char*>(v.data());
+  blob.insert(blob.end(), p, p + v.size() * sizeof(T));
+  return off;
+}
+std::string canon_element(const std::string& e) {
+  std::string o = e;
+  for (size_t i = 0; i < o.size(); ++i) o[i] = i == 0 ? (char)std::toupper((unsigned char)o[i]) : (char)std::tolower((unsigned char)o[i]);
+  return o;
+}
+}  // namespace
+
+CompiledMech compile_mechanism(const MechanismDef& D, const std::string& constants_name) {
+  const ConstantSet& cs = constant_set(constants_name.empty() ? kDefaultConstants : constants_name);
+  if (D.u_length != "cm" || D.u_quantity != "mol" || D.u_act_energy != "cal/mol" || D.u_time != "s")
+    throw MechError("unsupported CTI unit system (only length=cm, time=s, quantity=mol, act_energy=cal/mol)");
+  CompiledMech C;
+  C.constants = cs.name;
+  C.gas_constant = cs.gas_constant;
+  C.p_ref = cs.one_atm;
+  const int K = C.K = (int)D.species.size();
+  const int R = C.R = (int)D.reactions.size();
+  if (K < 1 || K > 250) throw MechError("species count out of range (1..250)");
+  if (R < 1 || R > 65000) throw MechError("reaction count out of range");
+  C.KP = ((K + 1 + 31) / 32) * 32;  // room for the "no species" sentinel slot K
+  C.elements = D.elements;
+  std::map<std::string, int> sp_index;
+  for (int k = 0; k < K; ++k) {
+    if (sp_index.count(D.species[k].name)) throw MechError("duplicate species " + D.species[k].name);
+    sp_index[D.species[k].name] = k;
+    C.species_names.push_back(D.species[k].name);
+  }
+  // molecular weights
+  C.W.assign(K, 0.0);
+  C.natoms.assign((size_t)K * D.elements.size(), 0.0);
+  for (int k = 0; k < K; ++k) {
+    for (auto& a : D.species[k].atoms) {
+      std::string el = canon_element(a.first);
+      auto it = cs.weights.find(el);
+      if (it == cs.weights.end()) throw MechError("no atomic weight for element '" + a.first + "'");
+      C.W[k] += a.second * it->second;
+      for (size_t e = 0; e < D.elements.size(); ++e)
+        if (canon_element(D.elements[e]) == el) C.natoms[k * D.elements.size() + e] = a.second;
+    }
+  }
+  // device order: falloff | three-body | elementary  (stable within each class)
+  for (int pass = 0; pass < 3; ++pass)
+    for (int i = 0; i < R; ++i) {
+      RxnKind want = pass == 0 ? RxnKind::Falloff : pass == 1 ? RxnKind::ThreeBody : RxnKind::Elementary;
+      if (D.reactions[i].kind == want) C.perm.push_back(i);
+    }
+  C.inv_perm.assign(R, 0);
+  for (int d = 0; d < R; ++d) C.inv_perm[C.perm[d]] = d;
+  for (auto& r : D.reactions) {
+    C.equations.push_back(r.equation);
+    if (r.kind == RxnKind::Falloff) C.n_fall++;
+    if (r.kind == RxnKind::ThreeBody) C.n_3b++;
+  }
+  const int nf = C.n_fall, n3 = C.n_3b;
+  const double to_EaR = cs.cal_to_J * 1000.0 / cs.gas_constant;  // cal/mol -> J/kmol -> K
+
+  std::vector<double> rW(K), Tmid(K), nasa((size_t)2 * 7 * C.KP, 0.0);
+  for (int k = 0; k < K; ++k) {
+    rW[k] = 1.0 / C.W[k];
+    Tmid[k] = D.species[k].Tmid;
+    for (int c = 0; c < 7; ++c) {
+      nasa[(size_t)(0 * 7 + c) * C.KP + k] = D.species[k].a_lo[c];
+      nasa[(size_t)(1 * 7 + c) * C.KP + k] = D.species[k].a_hi[c];
+    }
+  }
+  std::vector<double> A(R), b(R), E(R), A0(nf), b0(nf), E0(nf), ta(nf), rt3(nf), rt1(nf), t2(nf), eff_val;
+  std::vector<int> eff_ptr(nf + n3 + 1, 0);
+  std::vector<unsigned char> eff_sp, ftype(nf, 0), rev(R), reac((size_t)3 * R, (unsigned char)K), prod((size_t)3 * R, (unsigned char)K);
+  std::vector<signed char> dn(R);
+  // species -> reaction lists with net stoichiometric coefficient
+  std::vector<std::vector<std::pair<int, int>>> sp_list(K);
+  for (int d = 0; d < R; ++d) {
+    const ReactionDef& r = D.reactions[C.perm[d]];
+    int order = 0, nprod = 0;
+    std::map<int, int> net;
+    int slot = 0;
+    for (auto& t : r.reactants) {
+      auto it = sp_index.find(t.first);
+      if (it == sp_index.end()) throw MechError("undeclared species '" + t.first + "' in: " + r.equation);
+      for (int c = 0; c < t.second; ++c) {
+        if (slot >= 3) throw MechError("more than 3 reactant molecules in: " + r.equation);
+        reac[(size_t)slot++ * R + d] = (unsigned char)it->second;
+      }
+      order += t.second;
+      net[it->second] -= t.second;
+    }
+    slot = 0;
+    for (auto& t : r.products) {
+      auto it = sp_index.find(t.first);
+      if (it == sp_index.end()) throw MechError("undeclared species '" + t.first + "' in: " + r.equation);
+      for (int c = 0; c < t.second; ++c) {
+        if (slot >= 3) throw MechError("more than 3 product molecules in: " + r.equation);
+        prod[(size_t)slot++ * R + d] = (unsigned char)it->second;
+      }
+      nprod += t.second;
+      net[it->second] += t.second;
+    }
+    for (auto& kv : net) if (kv.second != 0) sp_list[kv.first].emplace_back(d, kv.second);
+    dn[d] = (signed char)(nprod - order);
+    rev[d] = r.reversible ? 1 : 0;
+    // 1 mol/cm^3 = 1e3 kmol/m^3  =>  A_SI = A * (1e-3)^(m-1), m = molecularity incl. M
+    int m = order + (r.kind == RxnKind::ThreeBody ? 1 : 0);
+    A[d] = r.kf[0] * std::pow(1e-3, m - 1);
+    b[d] = r.kf[1];
+    E[d] = r.kf[2] * to_EaR;
+    if (r.kind == RxnKind::Falloff) {
+      A0[d] = r.kf0[0] * std::pow(1e-3, order);
+      b0[d] = r.kf0[1];
+      E0[d] = r.kf0[2] * to_EaR;
+      ftype[d] = r.troe ? 1 : 0;
+      ta[d] = r.troe_p[0];
+      rt3[d] = r.troe ? 1.0 / r.troe_p[1] : 0.0;
+      rt1[d] = r.troe ? 1.0 / r.troe_p[2] : 0.0;
+      t2[d] = r.troe_p[3];
+    }
+    if (r.kind != RxnKind::Elementary) {
+      for (auto& e : r.efficiencies) {
+        auto it = sp_index.find(e.first);
+        if (it == sp_index.end()) throw MechError("undeclared collider '" + e.first + "' in: " + r.equation);
+        eff_sp.push_back((unsigned char)it->second);
+        eff_val.push_back(e.second - 1.0);
+      }
+      eff_ptr[d + 1] = (int)eff_sp.size();
+    } else if (!r.efficiencies.empty()) {
+      throw MechError("efficiencies on an elementary reaction: " + r.equation);
+    }
+  }
+  std::vector<int> sp_ptr(K + 1, 0);
+  std::vector<unsigned short> sp_rxn;
+  std::vector<signed char> sp_nu;
+  for (int k = 0; k < K; ++k) {
+    for (auto& e : sp_list[k]) { sp_rxn.push_back((unsigned short)e.first); sp_nu.push_back((signed char)e.second); }
+    sp_ptr[k + 1] = (int)sp_rxn.size();
+  }
+  auto& o = C.off;
+  o.W = append(C.blob, C.W); o.rW = append(C.blob, rW); o.Tmid = append(C.blob, Tmid); o.nasa = append(C.blob, nasa);
+  o.A = append(C.blob, A); o.b = append(C.blob, b); o.E = append(C.blob, E);
+  o.A0 = append(C.blob, A0); o.b0 = append(C.blob, b0); o.E0 = append(C.blob, E0);
+  o.troe_a = append(C.blob, ta); o.troe_rt3 = append(C.blob, rt3); o.troe_rt1 = append(C.blob, rt1); o.troe_t2 = append(C.blob, t2);
+  o.eff_val = append(C.blob, eff_val); o.eff_ptr = append(C.blob, eff_ptr); o.sp_ptr = append(C.blob, sp_ptr);
+  o.sp_rxn = append(C.blob, sp_rxn); o.sp_nu = append(C.blob, sp_nu); o.dn = append(C.blob, dn);
+  o.eff_sp = append(C.blob, eff_sp); o.ftype = append(C.blob, ftype); o.rev = append(C.blob, rev);
+  o.reac = append(C.blob, reac); o.prod = append(C.blob, prod);
+  while (C.blob.size() % 16) C.blob.push_back(0);
+  o.n_eff = (int)eff_sp.size(); o.n_nnz = (int)sp_rxn.size(); o.total = (int)C.blob.size();
+
+  // ---- algorithmic flop model (FMA = 2, each fp64 exp/log/log10/pow = 20) ----
+  int n_rev = 0, n_troe = 0, n_stoich = 0;
+  for (auto& r : D.reactions) {
+    n_rev += r.reversible;
+    n_troe += (r.kind == RxnKind::Falloff && r.troe);
+    for (auto& t : r.reactants) n_stoich += t.second;
+    for (auto& t : r.products) n_stoich += t.second;
+  }
+  const int n_arr = R + nf;
+  C.n_transcendental = 1 /*lnT*/ + 2 /*ln p/pref, ln c0*/ + n_arr + n_rev + n_troe * 6;
+  double arith = 8.0 * K            /* clip, normalise, Y/W, c */
+                 + 31.0 * K         /* NASA-7 cp,h,s,g */
+                 + 6.0 * K          /* energy sums, dY/dt */
+                 + 5.0 * n_arr      /* Arrhenius argument + scale */
+                 + 10.0 * n_rev     /* delta g gather + Kc argument */
+                 + 2.0 * (double)eff_sp.size() + 2.0 * (nf + n3) + 24.0 * nf /* third body, falloff algebra */
+                 + 6.0 * R          /* concentration products, net */
+                 + 2.0 * n_stoich;  /* wdot scatter */
+  C.flops_rhs = arith + 20.0 * C.n_transcendental;
+  const int N = K + 1;
+  // analytic d(wdot)/dc assembly: each (species,reaction) entry touches <=6 slots (mul+fma = 3 flops),
+  // third-body rows K per entry, plus chain rule to (T,Y) K*K*3 and energy row; T column = one extra RHS.
+  C.flops_jac = C.flops_rhs + 6.0 * 3.0 * sp_rxn.size() + 3.0 * (double)K * K + 6.0 * K + 2.0 * K * (nf + n3) + 2.0 * (double)K * K;
+  C.flops_lu = 2.0 / 3.0 * (double)N * N * N;
+  C.flops_solve = 2.0 * (double)N * N;
+  return C;
+}
+
+}  // namespace ctb

@@ -1,0 +1,336 @@
+"""Host-side mirror of the reference's reactor application interface, batched.
+
+Names and argument meaning follow the reference:
+  Chemistry::ThermoKinetics            /root/reference/include/chemistry.hpp:207-226
+  Apps::Reactor::Type / Create         /root/reference/include/applications/reactors/base.hpp:21-27,
+                                       /root/reference/include/applications/reactors/factory.hpp:15-72
+  SUNDIALS::CVODE::Solver::Integrate   /root/reference/include/sundials/cvode/interface.hpp:297
+  Solver::Solution / Client::State     /root/reference/include/sundials/cvode/client.hpp:110-120
+  solver statistics                    /root/reference/include/sundials/cvode/types.hpp:175-228
+but every object holds n reactors instead of one; all arithmetic happens in the
+CUDA library behind the C ABI (include/chemtools_b200.h).
+"""
+import ctypes as C
+import enum
+
+import numpy as np
+
+from ._lib import CtError, check, dp, ip, lib, lp
+
+# CVODE return codes passed through unchanged (interface.cpp:448-475 of the reference)
+CV_SUCCESS, CV_TSTOP_RETURN = 0, 1
+CV_TOO_MUCH_WORK, CV_TOO_MUCH_ACC, CV_ERR_FAILURE, CV_CONV_FAILURE = -1, -2, -3, -4
+
+STAT_NAMES = ("nst", "nfe", "nsetups", "netf", "nni", "ncfn", "nje", "nfeLS")
+
+
+class Type(enum.IntEnum):
+    Const_Pres = 0
+    Const_Vol = 1
+    Const_Temp_Pres = 2
+    Const_Temp_Vol = 3
+    Table_Temp_Pres = 4  # prescribed T(t), p(t) (planned by the reference, README.md:18-20)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(dp)
+
+
+class ThermoKinetics:
+    """Chemistry::ThermoKinetics(mechanism): first ideal_gas phase of a .cti (or a compiled .ctm)."""
+
+    def __init__(self, mechanism, phase_id=None, constants=None):
+        st = C.c_int(0)
+        self._h = lib().ct_mech_load_ex(str(mechanism).encode(), None if phase_id is None else phase_id.encode(),
+                                        None if constants is None else constants.encode(), C.byref(st))
+        if not self._h:
+            raise CtError(st.value, lib().ct_last_error().decode())
+        L = lib()
+        self.n_species = L.ct_mech_n_species(self._h)
+        self.n_reactions = L.ct_mech_n_reactions(self._h)
+        self.species_names = [L.ct_mech_species_name(self._h, k).decode() for k in range(self.n_species)]
+        self.molecular_weights = np.zeros(self.n_species)
+        check(L.ct_mech_molecular_weights(self._h, _p(self.molecular_weights)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().ct_mech_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # Cantera-style accessors used by the reference's tests (tests/src/chemistry.cpp:250-322)
+    def nSpecies(self):
+        return self.n_species
+
+    def nReactions(self):
+        return self.n_reactions
+
+    def speciesIndex(self, name):
+        return lib().ct_mech_species_index(self._h, name.encode())
+
+    def speciesName(self, k):
+        return self.species_names[k]
+
+    def reactionString(self, i):
+        s = lib().ct_mech_reaction_equation(self._h, i)
+        return None if s is None else s.decode()
+
+    def getMolecularWeights(self):
+        return self.molecular_weights.copy()
+
+    def elements(self):
+        L = lib()
+        return [L.ct_mech_element_name(self._h, e).decode() for e in range(L.ct_mech_n_elements(self._h))]
+
+    def nAtoms(self, k, e):
+        return lib().ct_mech_n_atoms(self._h, k, e)
+
+    def gas_constant(self):
+        return lib().ct_mech_gas_constant(self._h)
+
+    def save_ctm(self, path):
+        check(lib().ct_mech_save_ctm(self._h, str(path).encode()))
+
+    def compiled_arrays(self):
+        R = self.n_reactions
+        perm = np.zeros(R, dtype=np.int32); A = np.zeros(R); b = np.zeros(R); E = np.zeros(R)
+        check(lib().ct_mech_compiled_arrays(self._h, perm.ctypes.data_as(ip), _p(A), _p(b), _p(E)))
+        return perm, A, b, E
+
+    def flop_model(self, reactor_type):
+        out = np.zeros(4)
+        check(lib().ct_mech_flop_model(self._h, int(reactor_type), _p(out)))
+        return dict(zip(("rhs", "jac", "lu", "solve"), out.tolist()))
+
+    def composition(self, spec):
+        """{'H2': 2, 'O2': 1} -> dense vector in species order (not normalised)."""
+        x = np.zeros(self.n_species)
+        for name, v in spec.items():
+            k = self.speciesIndex(name)
+            if k < 0:
+                raise KeyError("unknown species " + name)
+            x[k] = v
+        return x
+
+    def mass_fractions(self, X):
+        """setState_TPX + getMassFractions of the reference's caller (tests/src/reactor.cpp:57-59)."""
+        X = _f64(np.atleast_2d(X))
+        Y = np.zeros_like(X)
+        check(lib().ct_mech_mole_to_mass(self._h, X.shape[0], _p(X), _p(Y)))
+        return Y
+
+
+class ReactorBatch:
+    """n reactors of one Apps::Reactor::Type sharing one mechanism, integrated on the GPU."""
+
+    def __init__(self, reactor_type, chemistry, temperature, pressure, mass_fractions,
+                 relative_solver_tolerance=1e-8, absolute_solver_tolerance=1e-14, total_simulation_time=1e-3,
+                 max_num_steps=500, device_arrays=False):
+        self.chem = chemistry
+        self.type = Type(int(reactor_type))
+        self._keep = None
+        if device_arrays:
+            # torch CUDA tensors already resident in HBM (no H2D inside)
+            T, p, Y = temperature, pressure, mass_fractions
+            n = int(T.shape[0])
+            self._keep = (T, p, Y)
+        else:
+            T = _f64(np.atleast_1d(temperature)); p = _f64(np.atleast_1d(pressure)); Y = _f64(np.atleast_2d(mass_fractions))
+            n = T.shape[0]
+            if p.shape != (n,) or Y.shape != (n, chemistry.n_species):
+                raise ValueError("temperature/pressure/mass_fractions shapes disagree")
+        self.n = n
+        st = C.c_int(0)
+        self._h = lib().ct_batch_create(chemistry._h, int(self.type), n, C.byref(st))
+        if not self._h:
+            raise CtError(st.value, lib().ct_last_error().decode())
+        self.n_state = lib().ct_batch_n_state(self._h)
+        check(lib().ct_batch_set_tolerances(self._h, relative_solver_tolerance, absolute_solver_tolerance))
+        check(lib().ct_batch_set_stop_time(self._h, total_simulation_time))
+        check(lib().ct_batch_set_max_steps(self._h, max_num_steps))
+        self.t_end = total_simulation_time
+        if device_arrays:
+            check(lib().ct_batch_set_ic_device(self._h, T.data_ptr(), p.data_ptr(), Y.data_ptr()))
+        else:
+            check(lib().ct_batch_set_ic(self._h, _p(T), _p(p), _p(Y)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().ct_batch_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ---- options (Solver::Set* of interface.hpp:77-89)
+    def SetMaxNumSteps(self, n):
+        check(lib().ct_batch_set_max_steps(self._h, int(n)))
+
+    def SetMaxOrder(self, q):
+        check(lib().ct_batch_set_max_order(self._h, int(q)))
+
+    def SetJacobian(self, mode):
+        check(lib().ct_batch_set_jacobian(self._h, {"dq": 0, "analytic": 1}.get(mode, mode)))
+
+    def SetIgnition(self, mode, value):
+        check(lib().ct_batch_set_ignition(self._h, {"absolute": 0, "rise": 1}.get(mode, mode), float(value)))
+
+    def SetTable(self, t, T, p):
+        t = _f64(t); T = _f64(np.atleast_2d(T)); p = _f64(np.atleast_2d(p))
+        if T.shape != (self.n, t.shape[0]) or p.shape != T.shape:
+            raise ValueError("table shapes must be [n, nt]")
+        check(lib().ct_batch_set_tp_table(self._h, t.shape[0], _p(t), _p(T), _p(p)))
+
+    def SetOrder(self, order):
+        o = np.ascontiguousarray(order, dtype=np.int32)
+        if o.shape != (self.n,):
+            raise ValueError("order must be a permutation of range(n)")
+        check(lib().ct_batch_set_order(self._h, o.ctypes.data_as(ip)))
+
+    def SetStream(self, cuda_stream_ptr):
+        check(lib().ct_batch_set_stream(self._h, cuda_stream_ptr))
+
+    # ---- solve
+    def Integrate(self, time):
+        """CVode(..., CV_NORMAL) for every reactor; returns 0 / 1 / most negative per-reactor code."""
+        code = lib().ct_batch_integrate(self._h, float(time))
+        if code <= -100:
+            check(code)
+        return code
+
+    def IntegrateTrajectory(self, n_out):
+        traj = np.zeros((self.n, n_out, self.n_state))
+        code = lib().ct_batch_integrate_trajectory(self._h, int(n_out), _p(traj))
+        if code <= -100:
+            check(code)
+        return code, traj
+
+    def Solution(self):
+        out = np.zeros((self.n, self.n_state))
+        check(lib().ct_batch_get_state(self._h, _p(out)))
+        return out
+
+    State = Solution
+
+    def Temperature(self):
+        if self.type > Type.Const_Vol:
+            raise ValueError("temperature is not a state of this reactor type")
+        return self.Solution()[:, 0]
+
+    def MassFractions(self):
+        s = self.Solution()
+        return s[:, 1:] if self.type <= Type.Const_Vol else s
+
+    def Time(self):
+        out = np.zeros(self.n)
+        check(lib().ct_batch_get_time(self._h, _p(out)))
+        return out
+
+    def IgnitionDelay(self):
+        out = np.zeros(self.n)
+        check(lib().ct_batch_get_ignition(self._h, _p(out)))
+        return out
+
+    def Status(self):
+        out = np.zeros(self.n, dtype=np.int32)
+        check(lib().ct_batch_get_status(self._h, out.ctypes.data_as(ip)))
+        return out
+
+    def Statistics(self):
+        out = np.zeros((self.n, 8), dtype=np.int64)
+        check(lib().ct_batch_get_stats(self._h, out.ctypes.data_as(lp)))
+        return out
+
+    def LastKernelMs(self):
+        return lib().ct_batch_last_kernel_ms(self._h)
+
+    def LaunchCount(self):
+        return lib().ct_batch_launch_count(self._h)
+
+    def WarpsPerSM(self):
+        return lib().ct_batch_warps_per_sm(self._h)
+
+    # ---- stand-alone kernels
+    def RightHandSide(self, states, times=None, rates=False):
+        """Base/EnergyEnabled::RightHandSide for all reactors: returns (ydot, wdot[, qf, qr])."""
+        states = _f64(states)
+        if states.shape != (self.n, self.n_state):
+            raise ValueError("states must be [n, n_state]")
+        K, R = self.chem.n_species, self.chem.n_reactions
+        ydot = np.zeros_like(states); wdot = np.zeros((self.n, K))
+        qf = np.zeros((self.n, R)) if rates else None
+        qr = np.zeros((self.n, R)) if rates else None
+        tt = None if times is None else _f64(times)
+        check(lib().ct_rhs_eval(self._h, _p(states), _p(tt), _p(ydot), _p(wdot), _p(qf), _p(qr)))
+        return (ydot, wdot, qf, qr) if rates else (ydot, wdot)
+
+    def Jacobian(self, states, mode="analytic", times=None):
+        states = _f64(states)
+        J = np.zeros((self.n, self.n_state, self.n_state))
+        tt = None if times is None else _f64(times)
+        check(lib().ct_jacobian_eval(self._h, {"dq": 0, "analytic": 1}[mode], _p(states), _p(tt), _p(J)))
+        return J.transpose(0, 2, 1)  # column-major on the device -> J[n, i, j] = d f_i / d y_j
+
+    def time_rhs(self, states, reps=20):
+        ms = C.c_double()
+        check(lib().ct_rhs_time(self._h, _p(_f64(states)), reps, C.cast(C.byref(ms), dp)))
+        return ms.value
+
+    def time_jacobian(self, states, mode="analytic", reps=5):
+        ms = C.c_double()
+        check(lib().ct_jacobian_time(self._h, {"dq": 0, "analytic": 1}[mode], _p(_f64(states)), reps, C.cast(C.byref(ms), dp)))
+        return ms.value
+
+
+def Create(reactor_type, chemistry, temperature, pressure, mass_fractions, relative_solver_tolerance,
+           absolute_solver_tolerance, total_simulation_time, write_results=False, **kw):
+    """Apps::Reactor::Create (factory.hpp:15-72); scalars give a batch of one reactor."""
+    try:
+        rt = Type(int(reactor_type))
+    except ValueError:
+        raise ValueError("Invalid reactor")  # factory.hpp:68-70
+    return ReactorBatch(rt, chemistry, temperature, pressure, mass_fractions, relative_solver_tolerance,
+                        absolute_solver_tolerance, total_simulation_time, **kw)
+
+
+def lu_solve(A, b):
+    """Batched dense LU + solve on the device (A[n, N, N] row-major as numpy, b[n, N])."""
+    A = _f64(A); b = _f64(b)
+    n, N = b.shape
+    Acm = np.ascontiguousarray(A.transpose(0, 2, 1))
+    x = np.zeros_like(b); info = np.zeros(n, dtype=np.int32)
+    check(lib().ct_lu_solve(N, n, _p(Acm), _p(b), _p(x), info.ctypes.data_as(ip)))
+    return x, info
+
+
+def lu_time(N, n, reps=10, solves_per_factor=1):
+    ms = C.c_double()
+    check(lib().ct_lu_time(N, n, reps, solves_per_factor, C.cast(C.byref(ms), dp)))
+    return ms.value
+
+
+def measure_fp64_peak():
+    t = C.c_double()
+    check(lib().ct_measure_fp64_peak(C.cast(C.byref(t), dp)))
+    return t.value
+
+
+def roberts_selftest(t_out, rtol, atol3):
+    t_out = _f64(t_out); atol3 = _f64(atol3)
+    y = np.zeros((t_out.shape[0], 3)); st = np.zeros(8, dtype=np.int64)
+    check(lib().ct_roberts_selftest(t_out.shape[0], _p(t_out), rtol, _p(atol3), _p(y), st.ctypes.data_as(lp)))
+    return y, dict(zip(STAT_NAMES, st.tolist()))
+
+
+def device_count():
+    return lib().ct_device_count()
+
+
+def set_device(i):
+    check(lib().ct_set_device(int(i)))

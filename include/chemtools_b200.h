@@ -1,0 +1,144 @@
+/* chemtools_b200 — C ABI of the B200-native batched homogeneous-reactor integrator.
+ *
+ * Drop-in boundary for the reactor path of ahmades/ChemTools.  Each entry
+ * point names the reference interface it replaces (paths relative to the
+ * reference repository).  Plain pointers and sizes only; no exceptions cross
+ * this boundary: every call returns an int (0 = ok, 1 = reached stop time,
+ * < 0 = failure class, CVODE-style where one exists) and ct_last_error()
+ * gives the message.  Handles are not thread-safe individually; distinct
+ * batches / GPUs may be driven from distinct host threads.
+ *
+ * There is NO CPU fallback: every compute entry point fails with
+ * CT_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef CHEMTOOLS_B200_H
+#define CHEMTOOLS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ct_mech ct_mech;   /* Chemistry::ThermoKinetics (include/chemistry.hpp:207-226) */
+typedef struct ct_batch ct_batch; /* N x { Apps::Reactor::Base + SUNDIALS::CVODE::Solver } */
+
+/* Apps::Reactor::Type (include/applications/reactors/base.hpp:21-27); 4 = prescribed T(t),p(t) table reactor
+ * (BASELINE config 4; the reference only plans it, README.md:18-20). */
+enum { CT_CONST_PRES = 0, CT_CONST_VOL = 1, CT_CONST_TEMP_PRES = 2, CT_CONST_TEMP_VOL = 3, CT_TABLE_TP = 4 };
+
+/* return / status codes. 0, 1 and the negative CV_* values are CVODE's own, which the reference returns
+ * unchanged from IStrategy::Integrate (src/sundials/cvode/interface.cpp:454-475). */
+enum {
+  CT_SUCCESS = 0, CT_TSTOP_RETURN = 1, CT_TOO_MUCH_WORK = -1, CT_TOO_MUCH_ACC = -2, CT_ERR_FAILURE = -3,
+  CT_CONV_FAILURE = -4, CT_LSETUP_FAIL = -6, CT_ILL_INPUT = -22, CT_TOO_CLOSE = -27,
+  CT_ERR_INVALID = -100, CT_ERR_MECH = -101, CT_ERR_NO_DEVICE = -102, CT_ERR_CUDA = -103, CT_ERR_UNSUPPORTED = -104
+};
+
+enum { CT_JAC_DQ = 0 /* CVODE dense difference quotient, what the reference uses (interface.cpp:698-703) */,
+       CT_JAC_ANALYTIC = 1 /* default */ };
+
+const char* ct_last_error(void);
+const char* ct_version(void);
+
+/* ---- mechanism: Chemistry::Thermo::Create + Chemistry::Kinetics::Create (include/chemistry.hpp:71-78, :166-174).
+ * path: Cantera .cti (first ideal_gas phase when phase_id is NULL, as newPhase(file) does) or a compiled ".ctm".
+ * constants: NULL = "cantera-2.6"; "cantera-2.4" selects the older gas constant / atomic weights. */
+ct_mech* ct_mech_load(const char* path, const char* phase_id_or_null, int* status);
+ct_mech* ct_mech_load_ex(const char* path, const char* phase_id_or_null, const char* constants_or_null, int* status);
+void ct_mech_destroy(ct_mech*);
+int ct_mech_save_ctm(const ct_mech*, const char* path);
+int ct_mech_n_species(const ct_mech*);   /* ThermoPhase::nSpecies */
+int ct_mech_n_reactions(const ct_mech*); /* Kinetics::nReactions */
+int ct_mech_n_elements(const ct_mech*);
+int ct_mech_species_index(const ct_mech*, const char* name); /* ThermoPhase::speciesIndex; -1 if absent */
+const char* ct_mech_species_name(const ct_mech*, int k);     /* ThermoPhase::speciesName */
+const char* ct_mech_reaction_equation(const ct_mech*, int i);/* Kinetics::reactionString */
+const char* ct_mech_element_name(const ct_mech*, int e);
+double ct_mech_n_atoms(const ct_mech*, int k, int e);
+int ct_mech_molecular_weights(const ct_mech*, double* W /*K*/); /* ThermoPhase::getMolecularWeights (base.cpp:102) */
+double ct_mech_gas_constant(const ct_mech*);
+/* compiled-array access for tests (device reaction order + permutation to file order) */
+int ct_mech_compiled_arrays(const ct_mech*, int* perm /*R*/, double* A /*R*/, double* b /*R*/, double* EaR /*R*/);
+/* mole <-> mass fractions: what the reference's caller does with setState_TPX + getMassFractions
+ * (tests/src/reactor.cpp:57-59); n rows of K, normalised. */
+int ct_mech_mole_to_mass(const ct_mech*, int64_t n, const double* X, double* Y);
+/* algorithmic flops per call for the roofline: rhs, jac, lu, solve */
+int ct_mech_flop_model(const ct_mech*, int reactor_type, double out[4]);
+
+/* ---- device selection / plumbing (no reference counterpart; the reference is single-threaded CPU) */
+int ct_device_count(void);
+int ct_set_device(int ordinal);
+/* cudaStream_t to launch on (e.g. torch's current stream); NULL = default stream */
+int ct_batch_set_stream(ct_batch*, void* cuda_stream);
+
+/* ---- batch of reactors: Apps::Reactor::Create(Type, thermo, kinetics, T, p, Y, rtol, atol, t_end, write)
+ * (include/applications/reactors/factory.hpp:15-72) for n cases at once. The batch borrows the mechanism. */
+ct_batch* ct_batch_create(ct_mech*, int reactor_type, int64_t n, int* status);
+void ct_batch_destroy(ct_batch*);
+int ct_batch_n_state(const ct_batch*); /* K+1 ([T, Y...], base.cpp:202-208) or K (base.cpp:84-87) */
+/* initial conditions, host arrays: T [K], p [Pa], Y mass fractions row-major n x K */
+int ct_batch_set_ic(ct_batch*, const double* T, const double* p, const double* Y);
+/* same, arrays already resident in device memory (no H2D inside) */
+int ct_batch_set_ic_device(ct_batch*, const double* dT, const double* dp, const double* dY);
+/* Client::SetTolerances (client.hpp:122-134) via Base::SetSolverParameters (base.cpp:112-121) */
+int ct_batch_set_tolerances(ct_batch*, double rtol, double atol);
+/* Client::SetIntegrationTime(0, t_end) (base.cpp:119-120) -> CVodeSetStopTime (interface.cpp:334-343) */
+int ct_batch_set_stop_time(ct_batch*, double t_end);
+/* Solver::SetMaxNumSteps (interface.hpp:80; 500 default, the reactor test uses 20000) */
+int ct_batch_set_max_steps(ct_batch*, int64_t mxstep);
+/* Solver::SetMaxOrder (interface.hpp:83), 1..5 */
+int ct_batch_set_max_order(ct_batch*, int q);
+int ct_batch_set_jacobian(ct_batch*, int mode);
+/* ignition monitor: mode 0 = first crossing of T >= value (reference test: 1756 K, tests/src/reactor.cpp:130),
+ * mode 1 = T >= T0 + value (default, value = 400 K); located on the integrator's dense output */
+int ct_batch_set_ignition(ct_batch*, int mode, double value);
+/* prescribed T(t), p(t): common time grid t[nt], per-reactor values T[n x nt], p[n x nt] (CT_TABLE_TP only) */
+int ct_batch_set_tp_table(ct_batch*, int nt, const double* t, const double* T, const double* p);
+/* optional processing order of the work queue (a permutation of 0..n-1), e.g. most expensive first */
+int ct_batch_set_order(ct_batch*, const int32_t* order);
+
+/* Solver::Integrate(t) (interface.hpp:297; interface.cpp:454-475), CV_NORMAL semantics, all internal steps on the
+ * device. Callable repeatedly with increasing t_target (the 10 us cadence of tests/src/reactor.cpp:105-126).
+ * Returns 0 if every reactor returned CV_SUCCESS, 1 if every live reactor reached the stop time, else the most
+ * negative per-reactor code. */
+int ct_batch_integrate(ct_batch*, double t_target);
+/* one launch covering n_out equally spaced outputs t_k = (k+1) t_end / n_out; traj (host) n x n_out x N */
+int ct_batch_integrate_trajectory(ct_batch*, int n_out, double* traj);
+/* Solver::Solution() / Client::State() (client.hpp:110-120): n x N host array */
+int ct_batch_get_state(ct_batch*, double* out);
+int ct_batch_get_state_device(ct_batch*, const double** dptr);
+int ct_batch_get_time(ct_batch*, double* t /*n*/);
+int ct_batch_get_ignition(ct_batch*, double* tau /*n, NaN = not ignited*/);
+int ct_batch_get_status(ct_batch*, int32_t* status /*n*/);
+/* IStrategy::MainSolverStatistics / LinearSolverStatistics (interface.cpp:487-623): per reactor
+ * nst, nfe, nsetups, netf, nni, ncfn, nje, nfeLS */
+int ct_batch_get_stats(ct_batch*, int64_t* stats /*n x 8*/);
+/* device time of the last integrate launch in ms (CUDA events on the launch stream) and launch count so far */
+double ct_batch_last_kernel_ms(const ct_batch*);
+int64_t ct_batch_launch_count(const ct_batch*);
+int ct_batch_warps_per_sm(const ct_batch*);
+
+/* ---- stand-alone kernels (parity tests, ncu evidence) ---- */
+/* K1: Base/EnergyEnabled::RightHandSide for n states (host arrays). T0,p0,Y0 define the frozen quantities exactly
+ * as Reactor::Create does; states n x N; outputs ydot n x N, wdot n x K [kmol/m^3/s], qf/qr n x R (file order; may
+ * be NULL). times may be NULL (only CT_TABLE_TP uses it). */
+int ct_rhs_eval(ct_batch*, const double* states, const double* times, double* ydot, double* wdot, double* qf, double* qr);
+/* K2: Jacobian d(ydot)/d(state), column-major N x N per reactor; mode CT_JAC_DQ or CT_JAC_ANALYTIC */
+int ct_jacobian_eval(ct_batch*, int mode, const double* states, const double* times, double* J);
+/* K3: batched dense LU (partial pivoting) + solve; A column-major n x N x N, b n x N -> x */
+int ct_lu_solve(int N, int64_t n, const double* A, const double* b, double* x, int32_t* info);
+/* timing loops for the roofline report: run the kernel `reps` times on resident data, return mean ms per launch */
+int ct_rhs_time(ct_batch*, const double* states, int reps, double* ms);
+int ct_jacobian_time(ct_batch*, int mode, const double* states, int reps, double* ms);
+int ct_lu_time(int N, int64_t n, int reps, int solves_per_factor, double* ms);
+/* measured fp64 FMA peak of the current device in TFLOP/s (register-resident DFMA loop) */
+int ct_measure_fp64_peak(double* tflops);
+/* CVODE Roberts problem on the device stepper (golden file of the reference:
+ * tests/data/sundials_cvode/direct_dense_cvRoberts_dns.dat); y_out n_out x 3 */
+int ct_roberts_selftest(int n_out, const double* t_out, double rtol, const double* atol3, double* y_out, int64_t* stats8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHEMTOOLS_B200_H */
