@@ -80,8 +80,23 @@ CompiledMech compile_mechanism(const MechanismDef& D, const std::string& constan
     }
   C.inv_perm.assign(R, 0);
   for (int d = 0; d < R; ++d) C.inv_perm[C.perm[d]] = d;
+  // Kinetics::reactionString: Cantera rebuilds the text from its species->coefficient std::map, i.e. species in
+  // ASCII order on each side (the reference asserts that form, tests/src/chemistry.cpp:287, :299).
+  auto side_string = [](const std::vector<std::pair<std::string, int>>& terms, RxnKind kind) {
+    std::map<std::string, int> acc;
+    for (auto& t : terms) acc[t.first] += t.second;
+    std::string s;
+    for (auto& kv : acc) {
+      if (!s.empty()) s += " + ";
+      if (kv.second != 1) s += std::to_string(kv.second) + " ";
+      s += kv.first;
+    }
+    if (kind == RxnKind::ThreeBody) s += " + M";
+    if (kind == RxnKind::Falloff) s += " (+M)";
+    return s;
+  };
   for (auto& r : D.reactions) {
-    C.equations.push_back(r.equation);
+    C.equations.push_back(side_string(r.reactants, r.kind) + (r.reversible ? " <=> " : " => ") + side_string(r.products, r.kind));
     if (r.kind == RxnKind::Falloff) C.n_fall++;
     if (r.kind == RxnKind::ThreeBody) C.n_3b++;
   }

@@ -137,7 +137,10 @@ class Mechanism:
         self.Tmid = np.array([s["nasa_lo"]["T"][1] for s in src["species"]])
         rx = src["reactions"]
         nR = self.nR = len(rx)
-        self.equations = [r["equation"] for r in rx]
+        self.file_equations = [r["equation"] for r in rx]
+        # Kinetics::reactionString: Cantera rebuilds the equation from its species->coefficient std::map,
+        # i.e. species in ASCII order on each side (tests/src/chemistry.cpp:287 expects exactly that form)
+        self.equations = [self._reaction_string(r) for r in rx]
         kind = {"elementary": 0, "three_body": 1, "falloff": 2}
         self.rtype = np.array([kind[r["kind"]] for r in rx], dtype=np.int32)
         self.rev = np.array([1 if r["reversible"] else 0 for r in rx], dtype=np.int32)
@@ -180,6 +183,21 @@ class Mechanism:
                               _dp(self.Tmid), _ip(self.rtype), _ip(self.rev), _dp(A), _dp(b), _dp(E), _dp(A0), _dp(b0),
                               _dp(E0), _ip(ftype), _dp(_f64(troe)), _ip(self.rp), _ip(self.rs), _ip(self.pp), _ip(self.ps),
                               _ip(self.ep), _ip(self.es), _dp(self.ev))
+
+    @staticmethod
+    def _reaction_string(r):
+        def side(terms):
+            acc = {}
+            for name, c in terms:
+                acc[name] = acc.get(name, 0) + c
+            parts = [(name if c == 1 else "%g %s" % (c, name)) for name, c in sorted(acc.items())]
+            s = " + ".join(parts)
+            if r["kind"] == "three_body":
+                s += " + M"
+            elif r["kind"] == "falloff":
+                s += " (+M)"
+            return s
+        return side(r["reactants"]) + (" <=> " if r["reversible"] else " => ") + side(r["products"])
 
     def __del__(self):
         try:
