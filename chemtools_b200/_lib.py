@@ -66,6 +66,8 @@ def lib():
         "ct_batch_set_max_order": (i32, [vp, i32]),
         "ct_batch_set_jacobian": (i32, [vp, i32]),
         "ct_batch_set_ignition": (i32, [vp, i32, dbl]),
+        "ct_batch_set_linear_solver": (i32, [vp, i32]),
+        "ct_batch_set_jacobian_clip": (i32, [vp, dbl]),
         "ct_batch_set_tp_table": (i32, [vp, i32, dp, dp, dp]),
         "ct_batch_set_order": (i32, [vp, ip]),
         "ct_batch_integrate": (i32, [vp, dbl]),
@@ -81,10 +83,10 @@ def lib():
         "ct_batch_warps_per_sm": (i32, [vp]),
         "ct_rhs_eval": (i32, [vp, dp, dp, dp, dp, dp, dp]),
         "ct_jacobian_eval": (i32, [vp, i32, dp, dp, dp]),
-        "ct_lu_solve": (i32, [i32, i64, dp, dp, dp, ip]),
+        "ct_lu_solve": (i32, [i32, i64, dp, dp, dp, ip, i32]),
         "ct_rhs_time": (i32, [vp, dp, i32, dp]),
         "ct_jacobian_time": (i32, [vp, i32, dp, i32, dp]),
-        "ct_lu_time": (i32, [i32, i64, i32, i32, dp]),
+        "ct_lu_time": (i32, [i32, i64, i32, i32, i32, dp]),
         "ct_measure_fp64_peak": (i32, [dp]),
         "ct_roberts_selftest": (i32, [i32, dp, dbl, dp, dp, lp]),
     }

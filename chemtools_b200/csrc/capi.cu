@@ -61,8 +61,10 @@ MechDesc make_desc(const CompiledMech& C) {
   d.o_W = o.W; d.o_rW = o.rW; d.o_Tmid = o.Tmid; d.o_nasa = o.nasa; d.o_A = o.A; d.o_b = o.b; d.o_E = o.E; d.o_A0 = o.A0;
   d.o_b0 = o.b0; d.o_E0 = o.E0; d.o_ta = o.troe_a; d.o_rt3 = o.troe_rt3; d.o_rt1 = o.troe_rt1; d.o_t2 = o.troe_t2;
   d.o_eff_val = o.eff_val; d.o_eff_ptr = o.eff_ptr; d.o_sp_ptr = o.sp_ptr; d.o_sp_rxn = o.sp_rxn; d.o_sp_nu = o.sp_nu;
-  d.o_dn = o.dn; d.o_eff_sp = o.eff_sp; d.o_ftype = o.ftype; d.o_rev = o.rev; d.o_reac = o.reac; d.o_prod = o.prod;
+  d.o_eff_sp = o.eff_sp; d.o_ftype = o.ftype; d.o_stoich = o.stoich; d.o_ent = o.ent; d.o_pstart = o.pstart; d.o_pnplus = o.pnplus;
+  d.o_lpp = o.lpp; d.o_spp = o.spp; d.n_pieces = o.n_pieces;
   d.blob_bytes = o.total;
+  static_assert(sizeof(MechDesc) <= CT_HDR_BYTES, "MechDesc must fit the shared header");
   return d;
 }
 
@@ -110,8 +112,8 @@ struct ct_batch {
   int64_t n = 0;
   double rtol = 1e-8, atol = 1e-14, t_stop = 1e-3;
   int64_t mxstep = 500;
-  int max_order = 5, jac_mode = CT_JAC_ANALYTIC, ign_mode = 1;
-  double ign_value = 400.0;
+  int max_order = 5, jac_mode = CT_JAC_ANALYTIC, ign_mode = 1, linsol = LINSOL_INVERSE;
+  double ign_value = 400.0, jac_clip = 1.0;
   bool have_ic = false, fresh = true, roberts = false;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -142,11 +144,12 @@ int configure_launch(ct_batch* b) {
   const WarpLayout L = make_layout(b->N, d.R);
   const size_t slab = (size_t)L.doubles * sizeof(double);
   const size_t avail = (size_t)di.max_smem_optin;
-  if ((size_t)d.blob_bytes + slab > avail) return fail(CT_ERR_UNSUPPORTED, "mechanism too large for one SM's shared memory");
-  int w = (int)((avail - d.blob_bytes) / slab);
+  const size_t fixed = CT_HDR_BYTES + (size_t)d.blob_bytes;
+  if (fixed + slab > avail) return fail(CT_ERR_UNSUPPORTED, "mechanism too large for one SM's shared memory");
+  int w = (int)((avail - fixed) / slab);
   w = std::min(w, 16);
   b->wpb = w;
-  b->smem = d.blob_bytes + (size_t)w * slab;
+  b->smem = fixed + (size_t)w * slab;
   // persistent: one CTA per SM, never more warps than reactors
   int64_t need = (b->n + w - 1) / w;
   b->grid = (int)std::max<int64_t>(1, std::min<int64_t>(di.sms, need));
@@ -157,7 +160,7 @@ BatchArgs make_args(ct_batch* b) {
   BatchArgs a{};
   a.rt = b->roberts ? RT_ROBERTS : b->rt;
   a.N = b->N; a.jac_mode = b->jac_mode; a.max_order = b->max_order; a.ign_mode = b->ign_mode; a.fresh = b->fresh ? 1 : 0;
-  a.n_out = 0; a.n = b->n; a.mxstep = b->mxstep;
+  a.n_out = 0; a.n = b->n; a.mxstep = b->mxstep; a.linsol = b->linsol; a.jac_clip = b->jac_clip;
   a.T0 = b->pT0; a.p0 = b->pp0; a.rho0 = b->rho0.p;
   a.nt = b->nt; a.tab_t = b->tab_t.p; a.tab_T = b->tab_T.p; a.tab_p = b->tab_p.p;
   a.rtol = b->rtol; a.atol = b->atol; a.atol_vec = b->atol_vec.n ? b->atol_vec.p : nullptr;
@@ -374,6 +377,16 @@ int ct_batch_set_jacobian(ct_batch* b, int mode) {
   b->jac_mode = mode;
   return 0;
 }
+int ct_batch_set_linear_solver(ct_batch* b, int mode) {
+  if (!b || (mode != LINSOL_LU && mode != LINSOL_INVERSE)) return fail(CT_ERR_INVALID, "bad linear solver mode");
+  b->linsol = mode;
+  return 0;
+}
+int ct_batch_set_jacobian_clip(ct_batch* b, double thr) {
+  if (!b || !(thr >= 0.0)) return fail(CT_ERR_INVALID, "bad clip threshold");
+  b->jac_clip = thr;
+  return 0;
+}
 int ct_batch_set_ignition(ct_batch* b, int mode, double value) {
   if (!b || (mode != 0 && mode != 1)) return fail(CT_ERR_INVALID, "bad ignition mode");
   b->ign_mode = mode; b->ign_value = value;
@@ -484,7 +497,7 @@ static int standalone_cfg(ct_batch* b, int* wpb, int* grid, size_t* smem, bool n
   if (int r = configure_launch(b)) return r;
   *wpb = std::min(b->wpb, 8);
   const WarpLayout L = make_layout(b->N, b->mech->desc.R);
-  *smem = b->mech->desc.blob_bytes + (size_t)*wpb * L.doubles * sizeof(double);
+  *smem = CT_HDR_BYTES + b->mech->desc.blob_bytes + (size_t)*wpb * L.doubles * sizeof(double);
   DeviceInfo di;
   if (int r = device_info(di)) return r;
   *grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)di.sms * 1, (b->n + *wpb - 1) / *wpb));
@@ -590,7 +603,7 @@ int ct_jacobian_time(ct_batch* b, int mode, const double* states, int reps, doub
   return jac_launch(b, mode, b->tmp_in.p, nullptr, b->tmp_out.p, reps, ms);
 }
 
-static int lu_run(int N, int64_t n, const double* dA, const double* db, double* dx, int* dinfo, int reps, int solves, double* ms) {
+static int lu_run(int N, int64_t n, const double* dA, const double* db, double* dx, int* dinfo, int reps, int solves, double* ms, int linsol) {
   DeviceInfo di;
   if (int r = device_info(di)) return r;
   const WarpLayout L = make_layout(N, 4);
@@ -602,9 +615,9 @@ static int lu_run(int N, int64_t n, const double* dA, const double* db, double* 
   if (int r = set_smem(k_lu_solve, smem)) return r;
   cudaEvent_t e0, e1;
   CT_CUDA(cudaEventCreate(&e0)); CT_CUDA(cudaEventCreate(&e1));
-  if (ms) for (int w = 0; w < 2; ++w) k_lu_solve<<<grid, wpb * 32, smem>>>(N, n, dA, db, dx, dinfo, solves);
+  if (ms) for (int w = 0; w < 2; ++w) k_lu_solve<<<grid, wpb * 32, smem>>>(N, n, dA, db, dx, dinfo, solves, linsol);
   CT_CUDA(cudaEventRecord(e0));
-  for (int w = 0; w < reps; ++w) k_lu_solve<<<grid, wpb * 32, smem>>>(N, n, dA, db, dx, dinfo, solves);
+  for (int w = 0; w < reps; ++w) k_lu_solve<<<grid, wpb * 32, smem>>>(N, n, dA, db, dx, dinfo, solves, linsol);
   CT_CUDA(cudaEventRecord(e1));
   CT_CUDA(cudaDeviceSynchronize());
   CT_CUDA(cudaGetLastError());
@@ -615,7 +628,7 @@ static int lu_run(int N, int64_t n, const double* dA, const double* db, double* 
   return 0;
 }
 
-int ct_lu_solve(int N, int64_t n, const double* A, const double* b, double* x, int32_t* info) {
+int ct_lu_solve(int N, int64_t n, const double* A, const double* b, double* x, int32_t* info, int linsol) {
   if (int r = require_device()) return r;
   if (N < 1 || N > CT_NP || n < 0 || !A || !b || !x) return fail(CT_ERR_INVALID, "bad argument");
   DevBuf<double> dA, db, dx; DevBuf<int> dinfo;
@@ -623,12 +636,12 @@ int ct_lu_solve(int N, int64_t n, const double* A, const double* b, double* x, i
   CT_CUDA(cudaMemcpy(dA.p, A, (size_t)n * N * N * sizeof(double), cudaMemcpyHostToDevice));
   CT_CUDA(cudaMemcpy(db.p, b, (size_t)n * N * sizeof(double), cudaMemcpyHostToDevice));
   CT_CUDA(cudaMemset(dx.p, 0, (size_t)n * N * sizeof(double)));
-  if (n > 0) if (int r = lu_run(N, n, dA.p, db.p, dx.p, dinfo.p, 1, 1, nullptr)) return r;
+  if (n > 0) if (int r = lu_run(N, n, dA.p, db.p, dx.p, dinfo.p, 1, 1, nullptr, linsol)) return r;
   CT_CUDA(cudaMemcpy(x, dx.p, (size_t)n * N * sizeof(double), cudaMemcpyDeviceToHost));
   if (info) CT_CUDA(cudaMemcpy(info, dinfo.p, n * sizeof(int), cudaMemcpyDeviceToHost));
   return 0;
 }
-int ct_lu_time(int N, int64_t n, int reps, int solves, double* ms) {
+int ct_lu_time(int N, int64_t n, int reps, int solves, int linsol, double* ms) {
   if (int r = require_device()) return r;
   if (N < 1 || N > CT_NP || n < 1 || reps < 1 || !ms) return fail(CT_ERR_INVALID, "bad argument");
   std::vector<double> A((size_t)n * N * N), b((size_t)n * N, 1.0);
@@ -639,7 +652,7 @@ int ct_lu_time(int N, int64_t n, int reps, int solves, double* ms) {
   CT_CUDA(dA.alloc(A.size())); CT_CUDA(db.alloc(b.size())); CT_CUDA(dx.alloc(b.size())); CT_CUDA(dinfo.alloc(n));
   CT_CUDA(cudaMemcpy(dA.p, A.data(), A.size() * sizeof(double), cudaMemcpyHostToDevice));
   CT_CUDA(cudaMemcpy(db.p, b.data(), b.size() * sizeof(double), cudaMemcpyHostToDevice));
-  return lu_run(N, n, dA.p, db.p, dx.p, dinfo.p, reps, solves, ms);
+  return lu_run(N, n, dA.p, db.p, dx.p, dinfo.p, reps, solves, ms, linsol);
 }
 
 int ct_measure_fp64_peak(double* tflops) {

@@ -187,9 +187,59 @@ CompiledMech compile_mechanism(const MechanismDef& D, const std::string& constan
   o.A0 = append(C.blob, A0); o.b0 = append(C.blob, b0); o.E0 = append(C.blob, E0);
   o.troe_a = append(C.blob, ta); o.troe_rt3 = append(C.blob, rt3); o.troe_rt1 = append(C.blob, rt1); o.troe_t2 = append(C.blob, t2);
   o.eff_val = append(C.blob, eff_val); o.eff_ptr = append(C.blob, eff_ptr); o.sp_ptr = append(C.blob, sp_ptr);
-  o.sp_rxn = append(C.blob, sp_rxn); o.sp_nu = append(C.blob, sp_nu); o.dn = append(C.blob, dn);
-  o.eff_sp = append(C.blob, eff_sp); o.ftype = append(C.blob, ftype); o.rev = append(C.blob, rev);
-  o.reac = append(C.blob, reac); o.prod = append(C.blob, prod);
+  o.sp_rxn = append(C.blob, sp_rxn); o.sp_nu = append(C.blob, sp_nu);
+  o.eff_sp = append(C.blob, eff_sp); o.ftype = append(C.blob, ftype);
+  // packed stoichiometry: bytes 0-2 reactant slots, 3-5 product slots (K = none), 6 reversible, 7 dn + 2
+  std::vector<unsigned long long> stoich(R);
+  for (int d = 0; d < R; ++d) {
+    unsigned long long w = 0;
+    for (int sl = 0; sl < 3; ++sl) w |= (unsigned long long)reac[(size_t)sl * R + d] << (8 * sl);
+    for (int sl = 0; sl < 3; ++sl) w |= (unsigned long long)prod[(size_t)sl * R + d] << (8 * (3 + sl));
+    w |= (unsigned long long)rev[d] << 48;
+    w |= (unsigned long long)(unsigned char)(dn[d] + 2) << 56;
+    stoich[d] = w;
+  }
+  o.stoich = append(C.blob, stoich);
+  // balanced gather tables for wdot: the species-sorted entry list (|nu| = 2 entries duplicated) is cut at species
+  // boundaries and at multiples of ceil(nnz/32); lane l owns the pieces that start inside its chunk.
+  {
+    std::vector<unsigned short> ent, pstart, pnplus;
+    std::vector<unsigned char> lpp(33, 0), spp(K + 1, 0);
+    std::vector<std::vector<std::pair<int, int>>> flat(K);  // per species: (reaction, sign) with duplicates
+    size_t nnz = 0;
+    for (int k = 0; k < K; ++k)
+      for (auto& e : sp_list[k])
+        for (int c = 0; c < std::abs(e.second); ++c) { flat[k].emplace_back(e.first, e.second > 0 ? 1 : -1); ++nnz; }
+    const size_t chunk = std::max<size_t>(1, (nnz + 31) / 32);
+    size_t pos = 0;
+    std::vector<int> piece_lane;
+    for (int k = 0; k < K; ++k) {
+      spp[k] = (unsigned char)pstart.size();
+      size_t i = 0;
+      while (i < flat[k].size()) {
+        const size_t room = chunk - (pos % chunk);
+        const size_t len = std::min(room, flat[k].size() - i);
+        pstart.push_back((unsigned short)ent.size());
+        piece_lane.push_back((int)(pos / chunk));
+        unsigned short np = 0;
+        for (size_t j = i; j < i + len; ++j) if (flat[k][j].second > 0) { ent.push_back((unsigned short)flat[k][j].first); ++np; }
+        for (size_t j = i; j < i + len; ++j) if (flat[k][j].second < 0) ent.push_back((unsigned short)flat[k][j].first);
+        pnplus.push_back(np);
+        i += len; pos += len;
+      }
+    }
+    spp[K] = (unsigned char)pstart.size();
+    const int P = (int)pstart.size();
+    if (P > 128 || P > 250) throw MechError("too many gather pieces for the shared partial buffer");
+    pstart.push_back((unsigned short)ent.size());
+    for (int l = 0; l <= 32; ++l) {
+      int first = P;
+      for (int pc = P - 1; pc >= 0; --pc) if (piece_lane[pc] >= l) first = pc;
+      lpp[l] = (unsigned char)first;
+    }
+    o.ent = append(C.blob, ent); o.pstart = append(C.blob, pstart); o.pnplus = append(C.blob, pnplus);
+    o.lpp = append(C.blob, lpp); o.spp = append(C.blob, spp); o.n_pieces = P;
+  }
   while (C.blob.size() % 16) C.blob.push_back(0);
   o.n_eff = (int)eff_sp.size(); o.n_nnz = (int)sp_rxn.size(); o.total = (int)C.blob.size();
 

@@ -81,7 +81,7 @@ struct CompiledMech {
   std::vector<unsigned char> blob;
   struct Offsets {
     int W, rW, Tmid, nasa, A, b, E, A0, b0, E0, troe_a, troe_rt3, troe_rt1, troe_t2, eff_val, eff_ptr,
-        sp_ptr, sp_rxn, sp_nu, dn, eff_sp, ftype, rev, reac, prod, n_eff, n_nnz, total;
+        sp_ptr, sp_rxn, sp_nu, eff_sp, ftype, stoich, ent, pstart, pnplus, lpp, spp, n_pieces, n_eff, n_nnz, total;
   } off{};
   // roofline bookkeeping: algorithmic flop counts per call (SURVEY.md §8d contract)
   double flops_rhs = 0, flops_jac = 0, flops_lu = 0, flops_solve = 0;

@@ -178,6 +178,12 @@ class ReactorBatch:
     def SetJacobian(self, mode):
         check(lib().ct_batch_set_jacobian(self._h, {"dq": 0, "analytic": 1}.get(mode, mode)))
 
+    def SetLinearSolver(self, mode):
+        check(lib().ct_batch_set_linear_solver(self._h, {"lu": 0, "inverse": 1}.get(mode, mode)))
+
+    def SetJacobianClip(self, thr):
+        check(lib().ct_batch_set_jacobian_clip(self._h, float(thr)))
+
     def SetIgnition(self, mode, value):
         check(lib().ct_batch_set_ignition(self._h, {"absolute": 0, "rise": 1}.get(mode, mode), float(value)))
 
@@ -299,19 +305,19 @@ def Create(reactor_type, chemistry, temperature, pressure, mass_fractions, relat
                         absolute_solver_tolerance, total_simulation_time, **kw)
 
 
-def lu_solve(A, b):
-    """Batched dense LU + solve on the device (A[n, N, N] row-major as numpy, b[n, N])."""
+def lu_solve(A, b, mode="lu"):
+    """Batched dense solve on the device (A[n, N, N] row-major as numpy, b[n, N]); mode "lu" or "inverse"."""
     A = _f64(A); b = _f64(b)
     n, N = b.shape
     Acm = np.ascontiguousarray(A.transpose(0, 2, 1))
     x = np.zeros_like(b); info = np.zeros(n, dtype=np.int32)
-    check(lib().ct_lu_solve(N, n, _p(Acm), _p(b), _p(x), info.ctypes.data_as(ip)))
+    check(lib().ct_lu_solve(N, n, _p(Acm), _p(b), _p(x), info.ctypes.data_as(ip), {"lu": 0, "inverse": 1}[mode]))
     return x, info
 
 
-def lu_time(N, n, reps=10, solves_per_factor=1):
+def lu_time(N, n, reps=10, solves_per_factor=1, mode="lu"):
     ms = C.c_double()
-    check(lib().ct_lu_time(N, n, reps, solves_per_factor, C.cast(C.byref(ms), dp)))
+    check(lib().ct_lu_time(N, n, reps, solves_per_factor, {"lu": 0, "inverse": 1}[mode], C.cast(C.byref(ms), dp)))
     return ms.value
 
 

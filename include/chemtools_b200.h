@@ -35,6 +35,7 @@ enum {
   CT_ERR_INVALID = -100, CT_ERR_MECH = -101, CT_ERR_NO_DEVICE = -102, CT_ERR_CUDA = -103, CT_ERR_UNSUPPORTED = -104
 };
 
+enum { CT_LINSOL_LU = 0, CT_LINSOL_INVERSE = 1 };
 enum { CT_JAC_DQ = 0 /* CVODE dense difference quotient, what the reference uses (interface.cpp:698-703) */,
        CT_JAC_ANALYTIC = 1 /* default */ };
 
@@ -90,6 +91,12 @@ int ct_batch_set_max_steps(ct_batch*, int64_t mxstep);
 /* Solver::SetMaxOrder (interface.hpp:83), 1..5 */
 int ct_batch_set_max_order(ct_batch*, int q);
 int ct_batch_set_jacobian(ct_batch*, int mode);
+/* Newton linear algebra: CT_LINSOL_LU = LU + triangular solves (what SUNLinSol_Dense does, interface.cpp:714-721),
+ * CT_LINSOL_INVERSE (default) = Gauss-Jordan inverse of I - gamma*J once per setup, each solve one mat-vec */
+int ct_batch_set_linear_solver(ct_batch*, int mode);
+/* analytic Jacobian: the column of species j is zeroed iff y_j * ewt_j < -thr (Cantera clips negative mass
+ * fractions, so the right-hand side does not depend on them); default 1 */
+int ct_batch_set_jacobian_clip(ct_batch*, double thr);
 /* ignition monitor: mode 0 = first crossing of T >= value (reference test: 1756 K, tests/src/reactor.cpp:130),
  * mode 1 = T >= T0 + value (default, value = 400 K); located on the integrator's dense output */
 int ct_batch_set_ignition(ct_batch*, int mode, double value);
@@ -126,12 +133,13 @@ int ct_batch_warps_per_sm(const ct_batch*);
 int ct_rhs_eval(ct_batch*, const double* states, const double* times, double* ydot, double* wdot, double* qf, double* qr);
 /* K2: Jacobian d(ydot)/d(state), column-major N x N per reactor; mode CT_JAC_DQ or CT_JAC_ANALYTIC */
 int ct_jacobian_eval(ct_batch*, int mode, const double* states, const double* times, double* J);
-/* K3: batched dense LU (partial pivoting) + solve; A column-major n x N x N, b n x N -> x */
-int ct_lu_solve(int N, int64_t n, const double* A, const double* b, double* x, int32_t* info);
+/* K3: batched dense LU (partial pivoting) + solve, or Gauss-Jordan inverse + mat-vec (linsol); A column-major
+ * n x N x N, b n x N -> x */
+int ct_lu_solve(int N, int64_t n, const double* A, const double* b, double* x, int32_t* info, int linsol);
 /* timing loops for the roofline report: run the kernel `reps` times on resident data, return mean ms per launch */
 int ct_rhs_time(ct_batch*, const double* states, int reps, double* ms);
 int ct_jacobian_time(ct_batch*, int mode, const double* states, int reps, double* ms);
-int ct_lu_time(int N, int64_t n, int reps, int solves_per_factor, double* ms);
+int ct_lu_time(int N, int64_t n, int reps, int solves_per_factor, int linsol, double* ms);
 /* measured fp64 FMA peak of the current device in TFLOP/s (register-resident DFMA loop) */
 int ct_measure_fp64_peak(double* tflops);
 /* CVODE Roberts problem on the device stepper (golden file of the reference:

@@ -24,8 +24,10 @@ MechDesc desc_of(const CompiledMech& C) {
   d.o_W = o.W; d.o_rW = o.rW; d.o_Tmid = o.Tmid; d.o_nasa = o.nasa; d.o_A = o.A; d.o_b = o.b; d.o_E = o.E; d.o_A0 = o.A0;
   d.o_b0 = o.b0; d.o_E0 = o.E0; d.o_ta = o.troe_a; d.o_rt3 = o.troe_rt3; d.o_rt1 = o.troe_rt1; d.o_t2 = o.troe_t2;
   d.o_eff_val = o.eff_val; d.o_eff_ptr = o.eff_ptr; d.o_sp_ptr = o.sp_ptr; d.o_sp_rxn = o.sp_rxn; d.o_sp_nu = o.sp_nu;
-  d.o_dn = o.dn; d.o_eff_sp = o.eff_sp; d.o_ftype = o.ftype; d.o_rev = o.rev; d.o_reac = o.reac; d.o_prod = o.prod;
+  d.o_eff_sp = o.eff_sp; d.o_ftype = o.ftype; d.o_stoich = o.stoich; d.o_ent = o.ent; d.o_pstart = o.pstart; d.o_pnplus = o.pnplus;
+  d.o_lpp = o.lpp; d.o_spp = o.spp; d.n_pieces = o.n_pieces;
   d.blob_bytes = o.total;
+  static_assert(sizeof(MechDesc) <= CT_HDR_BYTES, "MechDesc must fit the shared header");
   return d;
 }
 }  // namespace
@@ -60,7 +62,7 @@ int emu_rhs(void* mv, int rt, long long n, const double* T0, const double* p0, c
   BatchArgs a{};
   a.rt = rt; a.N = N; a.n = n; a.T0 = T0; a.p0 = p0; a.rho0 = rho0.data(); a.rtol = 1e-8; a.atol = 1e-14;
   const WarpLayout L = make_layout(N, m->d.R);
-  const size_t smem = m->d.blob_bytes + (size_t)L.doubles * 8;
+  const size_t smem = CT_HDR_BYTES + m->d.blob_bytes + (size_t)L.doubles * 8;
   emu_launch(k_rhs, 1, 32, smem, m->d, (const unsigned char*)m->C.blob.data(), a, states, (const double*)nullptr, ydot, wdot, qf, qr,
              (const int*)m->C.perm.data());
   return 0;
@@ -73,24 +75,24 @@ int emu_jacobian(void* mv, int rt, int mode, long long n, const double* T0, cons
   std::vector<double> st0((size_t)n * N), rho0(n), scratch(warp_scratch_doubles(N, m->d.R));
   run_init(m, rt, n, T0, p0, Y0, st0.data(), rho0.data(), N);
   BatchArgs a{};
-  a.rt = rt; a.N = N; a.n = n; a.T0 = T0; a.p0 = p0; a.rho0 = rho0.data(); a.rtol = 1e-8; a.atol = 1e-14; a.jac_mode = mode;
+  a.rt = rt; a.N = N; a.n = n; a.T0 = T0; a.p0 = p0; a.rho0 = rho0.data(); a.rtol = 1e-8; a.atol = 1e-14; a.jac_mode = mode; a.jac_clip = 1.0;
   a.scratch = scratch.data();
   const WarpLayout L = make_layout(N, m->d.R);
-  const size_t smem = m->d.blob_bytes + (size_t)L.doubles * 8;
+  const size_t smem = CT_HDR_BYTES + m->d.blob_bytes + (size_t)L.doubles * 8;
   emu_launch(k_jacobian, 1, 32, smem, m->d, (const unsigned char*)m->C.blob.data(), a, states, (const double*)nullptr, 1e-8, J);
   return 0;
 }
 
-int emu_lu_solve(int N, long long n, const double* A, const double* b, double* x, int* info) {
+int emu_lu_solve(int N, long long n, const double* A, const double* b, double* x, int* info, int linsol) {
   const WarpLayout L = make_layout(N, 4);
-  emu_launch(k_lu_solve, 1, 32, (size_t)L.doubles * 8, N, n, A, b, x, info, 1);
+  emu_launch(k_lu_solve, 1, 32, (size_t)L.doubles * 8, N, n, A, b, x, info, 1, linsol);
   return 0;
 }
 
 int emu_integrate(void* mv, int rt, long long n, const double* T0, const double* p0, const double* Y0, double rtol, double atol,
                   double t_end, long long mxstep, int jac_mode, int ign_mode, double ign_value, int n_out, int n_calls,
                   int nt, const double* tab_t, const double* tab_T, const double* tab_p,
-                  double* traj, double* state, double* tau, long long* stats, int* status, int warps) {
+                  double* traj, double* state, double* tau, long long* stats, int* status, int warps, int linsol, double jac_clip) {
   EmuMech* m = (EmuMech*)mv;
   const int N = rt <= 1 ? m->C.K + 1 : m->C.K;
   std::vector<double> rho0(n), tcur(n);
@@ -103,10 +105,10 @@ int emu_integrate(void* mv, int rt, long long n, const double* T0, const double*
   a.mxstep = mxstep; a.T0 = T0; a.p0 = p0; a.rho0 = rho0.data(); a.rtol = rtol; a.atol = atol; a.t_target = t_end; a.t_stop = t_end;
   a.nt = nt; a.tab_t = tab_t; a.tab_T = tab_T; a.tab_p = tab_p;
   a.ign_value = ign_value; a.state = state; a.traj = traj; a.tau = tau; a.tcur = tcur.data(); a.stats = stats; a.status = status;
-  a.counter = &counter; a.scratch = scratch.data();
+  a.counter = &counter; a.scratch = scratch.data(); a.linsol = linsol; a.jac_clip = jac_clip;
   a.save_stride = CT_LMAX * CT_NP + CT_SAVE_SCALARS;
   const WarpLayout L = make_layout(N, m->d.R);
-  const size_t smem = m->d.blob_bytes + (size_t)warps * L.doubles * 8;
+  const size_t smem = CT_HDR_BYTES + m->d.blob_bytes + (size_t)warps * L.doubles * 8;
   std::vector<double> save;
   for (long long i = 0; i < n; ++i) status[i] = 0;
   if (n_calls <= 1) {
@@ -137,9 +139,9 @@ int emu_roberts(int n_out, const double* t_out, double rtol, const double* atol3
   a.rt = RT_ROBERTS; a.N = 3; a.jac_mode = JAC_ANALYTIC; a.max_order = 5; a.fresh = 1; a.n_out = n_out; a.n = 1; a.mxstep = 500;
   a.rtol = rtol; a.atol = 0.0; a.atol_vec = atol3; a.t_target = 1e300; a.t_stop = 1e300; a.state = state; a.traj = y_out;
   a.tau = &tau; a.tcur = &tcur; a.stats = stats8; a.status = &status; a.counter = &counter; a.scratch = scratch.data();
-  a.out_times = t_out;
+  a.out_times = t_out; a.linsol = LINSOL_LU;
   const WarpLayout L = make_layout(3, 0);
-  emu_launch(k_integrate<256>, 1, 32, (size_t)L.doubles * 8, d, (const unsigned char*)nullptr, a);
+  emu_launch(k_integrate<256>, 1, 32, CT_HDR_BYTES + (size_t)L.doubles * 8, d, (const unsigned char*)nullptr, a);
   return status;
 }
 

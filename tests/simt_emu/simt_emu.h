@@ -20,6 +20,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __restrict__
 #define __launch_bounds__(...)
 
@@ -85,7 +86,7 @@ inline double exp10(double x) { return std::pow(10.0, x); }
 inline double __ldg(const double* p) { return *p; }
 using std::fabs; using std::fmax; using std::fmin; using std::log; using std::exp; using std::sqrt; using std::pow; using std::log10;
 
-inline unsigned char* emu_dynamic_smem() { return emu_blk->smem; }
+inline thread_local unsigned char* emu_smem_base = nullptr;  // what kernels.cuh's ct_smem resolves to
 
 // Launch: blocks run one after another, threads of a block concurrently.
 template <class Kernel, class... Args>
@@ -101,7 +102,7 @@ void emu_launch(Kernel k, unsigned grid, unsigned block, size_t smem_bytes, Args
     for (unsigned t = 0; t < block; ++t) {
       th.emplace_back([&, t, b]() {
         threadIdx.x = t; blockIdx.x = b; blockDim.x = block; gridDim.x = grid;
-        emu_blk = &blk; emu_wp = &blk.warps[t / 32]; emu_lane = (int)(t % 32);
+        emu_blk = &blk; emu_wp = &blk.warps[t / 32]; emu_lane = (int)(t % 32); emu_smem_base = blk.smem;
         k(args...);
       });
     }
