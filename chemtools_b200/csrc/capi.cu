@@ -112,7 +112,7 @@ struct ct_batch {
   int64_t n = 0;
   double rtol = 1e-8, atol = 1e-14, t_stop = 1e-3;
   int64_t mxstep = 500;
-  int max_order = 5, jac_mode = CT_JAC_ANALYTIC, ign_mode = 1, linsol = LINSOL_INVERSE;
+  int max_order = 5, jac_mode = CT_JAC_ANALYTIC, ign_mode = 1, linsol = LINSOL_LU;
   double ign_value = 400.0, jac_clip = 1.0;
   bool have_ic = false, fresh = true, roberts = false;
   cudaStream_t stream = nullptr;
