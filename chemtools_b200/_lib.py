@@ -52,6 +52,19 @@ def lib():
         "ct_mech_compiled_arrays": (i32, [vp, ip, dp, dp, dp]),
         "ct_mech_mole_to_mass": (i32, [vp, i64, dp, dp]),
         "ct_mech_flop_model": (i32, [vp, i32, dp]),
+        "ct_input_parse": (vp, [cs, C.POINTER(C.c_int)]),
+        "ct_input_destroy": (None, [vp]),
+        "ct_input_n_case_sets": (i32, [vp, i32]),
+        "ct_input_n_cases": (i32, [vp, i32, i32]),
+        "ct_input_mechanism_path": (cs, [vp, i32, i32]),
+        "ct_input_mechanism_description": (cs, [vp, i32, i32]),
+        "ct_input_set_description": (cs, [vp, i32, i32]),
+        "ct_input_case_description": (cs, [vp, i32, i32, i32]),
+        "ct_input_case": (i32, [vp, i32, i32, i32, dp, dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "ct_input_case_species": (cs, [vp, i32, i32, i32, i32, dp]),
+        "ct_input_case_mass_fractions": (i32, [vp, i32, i32, i32, vp, dp]),
+        "ct_input_n_warnings": (i32, [vp]),
+        "ct_input_warning": (cs, [vp, i32]),
         "ct_device_count": (i32, []),
         "ct_set_device": (i32, [i32]),
         "ct_batch_set_stream": (i32, [vp, vp]),

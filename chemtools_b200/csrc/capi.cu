@@ -13,7 +13,10 @@
 
 #include "../../include/chemtools_b200.h"
 #include "kernels.cuh"
+#include "input_parser.hpp"
 #include "mechanism.hpp"
+
+#include <sys/stat.h>
 
 using namespace ctb;
 
@@ -226,9 +229,89 @@ int summarize_status(ct_batch* b, int* out) {
 
 }  // namespace
 
+struct ct_input {
+  InputParameters P;
+  std::vector<std::string> warnings;
+  std::vector<InputCaseSet>& sets(int type) { return type == 0 ? P.const_P : type == 1 ? P.const_V : type == 2 ? P.const_TP : P.const_TV; }
+  const InputCaseSet* set(int type, int i) {
+    if (type < 0 || type > 3) return nullptr;
+    auto& v = sets(type);
+    return (i >= 0 && i < (int)v.size()) ? &v[i] : nullptr;
+  }
+  const InputCase* cas(int type, int i, int c) {
+    const InputCaseSet* s = set(type, i);
+    return (s && c >= 0 && c < (int)s->cases.size()) ? &s->cases[c] : nullptr;
+  }
+};
+
 extern "C" {
 
 const char* ct_last_error(void) { return g_err.c_str(); }
+
+// ---------------------------------------------------------------- YAML input (Input::Parser)
+ct_input* ct_input_parse(const char* config_file, int* status) {
+  auto set = [&](int s) { if (status) *status = s; };
+  if (!config_file) { set(fail(CT_ERR_INVALID, "null config path")); return nullptr; }
+  try {
+    std::unique_ptr<ct_input> in(new ct_input);
+    in->P = parse_input(config_file);
+    // Parser::Validate (src/input_parser.cpp:310-351): mechanism file exists, then every case against its thermo
+    for (int t = 0; t < 4; ++t)
+      for (auto& cs : in->sets(t)) {
+        struct stat sb;
+        if (stat(cs.mechanism_path.c_str(), &sb) != 0) throw InputError(InputError::Filesystem, "Input error: " + cs.mechanism_path + ": No such file or directory");
+        const bool is_ctm = cs.mechanism_path.size() > 4 && cs.mechanism_path.compare(cs.mechanism_path.size() - 4, 4, ".ctm") == 0;
+        MechanismDef def = is_ctm ? read_ctm(cs.mechanism_path) : parse_cti(cs.mechanism_path, nullptr);
+        CompiledMech C = compile_mechanism(def, "");
+        double Tmin = 0.0, Tmax = 1e300;  // ThermoPhase::minTemp / maxTemp
+        for (auto& sp : def.species) { Tmin = std::max(Tmin, sp.Tlo); Tmax = std::min(Tmax, sp.Thi); }
+        for (auto& c : cs.cases) validate_case(c, C, Tmin, Tmax, &in->warnings);
+      }
+    set(0);
+    return in.release();
+  } catch (const InputError& e) {
+    static const int codes[] = {CT_ERR_INVALID, CT_ERR_YAML_BAD_FILE, CT_ERR_YAML_INVALID_NODE, CT_ERR_YAML_BAD_CONVERSION, CT_ERR_FILESYSTEM, CT_ERR_INPUT, CT_ERR_INPUT_UNIT};
+    set(fail(codes[e.kind], e.what()));
+  } catch (const std::exception& e) {
+    set(fail(CT_ERR_MECH, e.what()));
+  }
+  return nullptr;
+}
+void ct_input_destroy(ct_input* in) { delete in; }
+int ct_input_n_case_sets(ct_input* in, int type) { return (in && type >= 0 && type <= 3) ? (int)in->sets(type).size() : fail(CT_ERR_INVALID, "bad argument"); }
+int ct_input_n_cases(ct_input* in, int type, int set) { auto* s = in ? in->set(type, set) : nullptr; return s ? (int)s->cases.size() : fail(CT_ERR_INVALID, "bad case set"); }
+const char* ct_input_mechanism_path(ct_input* in, int type, int set) { auto* s = in ? in->set(type, set) : nullptr; return s ? s->mechanism_path.c_str() : nullptr; }
+const char* ct_input_mechanism_description(ct_input* in, int type, int set) { auto* s = in ? in->set(type, set) : nullptr; return (s && s->has_mechanism_description) ? s->mechanism_description.c_str() : nullptr; }
+const char* ct_input_set_description(ct_input* in, int type, int set) { auto* s = in ? in->set(type, set) : nullptr; return (s && s->has_description) ? s->description.c_str() : nullptr; }
+const char* ct_input_case_description(ct_input* in, int type, int set, int c) { auto* k = in ? in->cas(type, set, c) : nullptr; return (k && k->has_description) ? k->description.c_str() : nullptr; }
+int ct_input_case(ct_input* in, int type, int set, int c, double* pressure, double* temperature, double* time, int* comp_type, int* n_pairs) {
+  auto* k = in ? in->cas(type, set, c) : nullptr;
+  if (!k) return fail(CT_ERR_INVALID, "bad case index");
+  if (pressure) *pressure = k->pressure;
+  if (temperature) *temperature = k->temperature;
+  if (time) *time = k->time;
+  if (comp_type) *comp_type = (int)k->composition_type;
+  if (n_pairs) *n_pairs = (int)k->composition.size();
+  return 0;
+}
+const char* ct_input_case_species(ct_input* in, int type, int set, int c, int i, double* value) {
+  auto* k = in ? in->cas(type, set, c) : nullptr;
+  if (!k || i < 0 || i >= (int)k->composition.size()) return nullptr;
+  if (value) *value = k->composition[i].second;
+  return k->composition[i].first.c_str();
+}
+int ct_input_case_mass_fractions(ct_input* in, int type, int set, int c, const ct_mech* m, double* Y) {
+  auto* k = in ? in->cas(type, set, c) : nullptr;
+  if (!k || !m || !Y) return fail(CT_ERR_INVALID, "bad argument");
+  try {
+    std::vector<double> y = case_mass_fractions(*k, m->C);
+    std::copy(y.begin(), y.end(), Y);
+  } catch (const std::exception& e) { return fail(CT_ERR_INPUT, e.what()); }
+  return 0;
+}
+int ct_input_n_warnings(ct_input* in) { return in ? (int)in->warnings.size() : 0; }
+const char* ct_input_warning(ct_input* in, int i) { return (in && i >= 0 && i < (int)in->warnings.size()) ? in->warnings[i].c_str() : nullptr; }
+
 const char* ct_version(void) { return "chemtools_b200 0.1 (sm_100a)"; }
 
 ct_mech* ct_mech_load(const char* path, const char* phase_id, int* status) { return ct_mech_load_ex(path, phase_id, nullptr, status); }

@@ -32,7 +32,11 @@ enum { CT_CONST_PRES = 0, CT_CONST_VOL = 1, CT_CONST_TEMP_PRES = 2, CT_CONST_TEM
 enum {
   CT_SUCCESS = 0, CT_TSTOP_RETURN = 1, CT_TOO_MUCH_WORK = -1, CT_TOO_MUCH_ACC = -2, CT_ERR_FAILURE = -3,
   CT_CONV_FAILURE = -4, CT_LSETUP_FAIL = -6, CT_ILL_INPUT = -22, CT_TOO_CLOSE = -27,
-  CT_ERR_INVALID = -100, CT_ERR_MECH = -101, CT_ERR_NO_DEVICE = -102, CT_ERR_CUDA = -103, CT_ERR_UNSUPPORTED = -104
+  CT_ERR_INVALID = -100, CT_ERR_MECH = -101, CT_ERR_NO_DEVICE = -102, CT_ERR_CUDA = -103, CT_ERR_UNSUPPORTED = -104,
+  /* Input::Parser failures, one code per exception class the reference throws (tests/src/input_parser.cpp:27-94) */
+  CT_ERR_YAML_BAD_FILE = -110 /* YAML::BadFile */, CT_ERR_YAML_INVALID_NODE = -111 /* YAML::InvalidNode */,
+  CT_ERR_YAML_BAD_CONVERSION = -112 /* YAML::BadConversion */, CT_ERR_FILESYSTEM = -113 /* boost::filesystem::filesystem_error */,
+  CT_ERR_INPUT = -114 /* std::runtime_error */, CT_ERR_INPUT_UNIT = -115 /* std::invalid_argument */
 };
 
 enum { CT_LINSOL_LU = 0, CT_LINSOL_INVERSE = 1 };
@@ -66,6 +70,27 @@ int ct_mech_compiled_arrays(const ct_mech*, int* perm /*R*/, double* A /*R*/, do
 int ct_mech_mole_to_mass(const ct_mech*, int64_t n, const double* X, double* Y);
 /* algorithmic flops per call for the roofline: rhs, jac, lu, solve */
 int ct_mech_flop_model(const ct_mech*, int reactor_type, double out[4]);
+
+/* ---- YAML case-set input: Input::Parser(config) = Parse + Validate (include/input/parser.hpp:9-28,
+ * src/input_parser.cpp:147-170, :345-351).  reactor_type 0..3 selects Parameters.reactor.{const_P, const_V, const_TP,
+ * const_TV} (include/input/types.hpp:310-346).  Values come back converted: Pa, K, s, mol/m^3. */
+typedef struct ct_input ct_input;
+ct_input* ct_input_parse(const char* config_file, int* status);
+void ct_input_destroy(ct_input*);
+int ct_input_n_case_sets(ct_input*, int reactor_type);
+int ct_input_n_cases(ct_input*, int reactor_type, int set);
+const char* ct_input_mechanism_path(ct_input*, int reactor_type, int set);
+const char* ct_input_mechanism_description(ct_input*, int reactor_type, int set); /* NULL if not defined */
+const char* ct_input_set_description(ct_input*, int reactor_type, int set);       /* NULL if not defined */
+const char* ct_input_case_description(ct_input*, int reactor_type, int set, int cas);
+/* composition_type: 1 concentration, 2 mass fraction, 3 mole fraction (Input::CompositionInputType) */
+int ct_input_case(ct_input*, int reactor_type, int set, int cas, double* pressure, double* temperature, double* time,
+                  int* composition_type, int* n_pairs);
+const char* ct_input_case_species(ct_input*, int reactor_type, int set, int cas, int i, double* value);
+/* what the reference leaves to its (missing) driver: a case's composition as mass fractions in species order */
+int ct_input_case_mass_fractions(ct_input*, int reactor_type, int set, int cas, const ct_mech*, double* Y /*K*/);
+int ct_input_n_warnings(ct_input*);            /* temperature outside the mechanism's range warns, src/input_parser.cpp:199-211 */
+const char* ct_input_warning(ct_input*, int i);
 
 /* ---- device selection / plumbing (no reference counterpart; the reference is single-threaded CPU) */
 int ct_device_count(void);
