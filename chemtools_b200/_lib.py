@@ -65,6 +65,10 @@ def lib():
         "ct_input_case_mass_fractions": (i32, [vp, i32, i32, i32, vp, dp]),
         "ct_input_n_warnings": (i32, [vp]),
         "ct_input_warning": (cs, [vp, i32]),
+        "ct_h5_create": (vp, []),
+        "ct_h5_destroy": (None, [vp]),
+        "ct_h5_add_dataset": (i32, [vp, cs, i32, lp, dp, cs, cs, cs]),
+        "ct_h5_write": (i32, [vp, cs]),
         "ct_device_count": (i32, []),
         "ct_set_device": (i32, [i32]),
         "ct_batch_set_stream": (i32, [vp, vp]),

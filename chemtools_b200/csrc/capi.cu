@@ -13,6 +13,7 @@
 
 #include "../../include/chemtools_b200.h"
 #include "kernels.cuh"
+#include "h5_writer.hpp"
 #include "input_parser.hpp"
 #include "mechanism.hpp"
 
@@ -247,6 +248,31 @@ struct ct_input {
 extern "C" {
 
 const char* ct_last_error(void) { return g_err.c_str(); }
+
+// ---------------------------------------------------------------- results (Results::HDF5Writer layout)
+struct ct_h5 { H5File f; };
+ct_h5* ct_h5_create(void) { return new ct_h5; }
+void ct_h5_destroy(ct_h5* h) { delete h; }
+int ct_h5_add_dataset(ct_h5* h, const char* path, int rank, const int64_t* dims, const double* data, const char* name,
+                      const char* notation, const char* unit) {
+  if (!h || !path || rank < 0 || rank > 4 || (rank > 0 && !dims) || !data) return fail(CT_ERR_INVALID, "bad dataset arguments");
+  try {
+    std::vector<uint64_t> d(rank);
+    for (int i = 0; i < rank; ++i) { if (dims[i] < 0) return fail(CT_ERR_INVALID, "negative dimension"); d[i] = (uint64_t)dims[i]; }
+    std::vector<std::pair<std::string, std::string>> attrs;
+    // Results::Meta::Register(group, set, name, notation, unit, ptr) (include/results/observer.hpp:59-72)
+    if (name) attrs.emplace_back("Name", name);
+    if (notation) attrs.emplace_back("Notation", notation);
+    if (unit) attrs.emplace_back("Unit", unit);
+    h->f.create_dataset(path, d, data, attrs);
+  } catch (const std::exception& e) { return fail(CT_ERR_INVALID, e.what()); }
+  return 0;
+}
+int ct_h5_write(ct_h5* h, const char* filename) {
+  if (!h || !filename) return fail(CT_ERR_INVALID, "null argument");
+  try { h->f.write(filename); } catch (const std::exception& e) { return fail(CT_ERR_FILESYSTEM, e.what()); }
+  return 0;
+}
 
 // ---------------------------------------------------------------- YAML input (Input::Parser)
 ct_input* ct_input_parse(const char* config_file, int* status) {

@@ -92,6 +92,16 @@ int ct_input_case_mass_fractions(ct_input*, int reactor_type, int set, int cas, 
 int ct_input_n_warnings(ct_input*);            /* temperature outside the mechanism's range warns, src/input_parser.cpp:199-211 */
 const char* ct_input_warning(ct_input*, int i);
 
+/* ---- results: Results::HDF5Writer (src/results/hdf5_writer.cpp:136-217) — /<group>/<set> f64 datasets with the string
+ * attributes Name / Notation / Unit registered through Results::Meta::Register (include/results/observer.hpp:59-72).
+ * Groups are created from the path. rank 1 = one reactor's series, rank 2 = [reactor][sample]. */
+typedef struct ct_h5 ct_h5;
+ct_h5* ct_h5_create(void);
+void ct_h5_destroy(ct_h5*);
+int ct_h5_add_dataset(ct_h5*, const char* path, int rank, const int64_t* dims, const double* data, const char* name,
+                      const char* notation, const char* unit);
+int ct_h5_write(ct_h5*, const char* filename);
+
 /* ---- device selection / plumbing (no reference counterpart; the reference is single-threaded CPU) */
 int ct_device_count(void);
 int ct_set_device(int ordinal);

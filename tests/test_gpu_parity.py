@@ -338,3 +338,57 @@ def test_empty_and_error_paths(ctb, chem):
     b = ctb.ReactorBatch(1, ch, [1300.0, 900.0], [101325.0] * 2, Y, 1e-8, 1e-14, 1e-3, max_num_steps=50)
     assert b.Integrate(1e-3) == -1
     assert b.Status()[0] == -1
+
+
+def test_application_yaml_to_hdf5(ctb, chem, omech, tmp_path):
+    """The driver the reference lacks (src/main.cpp:5-12 is a stub): YAML case sets -> batches -> Integrate -> HDF5 in
+    the reference's layout; the reference test's own scenario (tests/src/reactor.cpp:50-64) written as a YAML case."""
+    import sys
+    sys.path.insert(0, str(__import__("pathlib").Path(__file__).parent))
+    from h5_min_reader import H5Min
+    from chemtools_b200 import app
+    mech = ctb.mechanism_path("gri30")
+    cfg = tmp_path / "config.yaml"
+    cfg.write_text("""- Reactor: CONSTANT_VOLUME
+  Mechanism:
+    Path: %s
+  Cases:
+    Case:
+      Description: reference reactor test
+      Pressure: {Unit: atm, Value: 1.0}
+      Temperature: {Unit: K, Value: 1001.0}
+      Composition:
+        Type: mole fraction
+        Value: [[H2, 0.2857142857142857], [O2, 0.14285714285714285], [N2, 0.5714285714285714]]
+      Time: {Unit: ms, Value: 1.0}
+    Case:
+      Description: hotter
+      Pressure: {Unit: bar, Value: 1.01325}
+      Temperature: {Unit: degC, Value: 926.85}
+      Composition:
+        Type: mole fraction
+        Value: [[H2, 0.2857142857142857], [O2, 0.14285714285714285], [N2, 0.5714285714285714]]
+      Time: {Unit: ms, Value: 1.0}
+- Reactor: CONSTANT_TEMPERATURE_PRESSURE
+  Mechanism:
+    Path: %s
+  Cases:
+    Case:
+      Pressure: {Unit: atm, Value: 1.0}
+      Temperature: {Unit: K, Value: 1500.0}
+      Composition: {Type: mass fraction, Value: [[CH4, 0.05], [O2, 0.2], [N2, 0.75]]}
+      Time: {Unit: us, Value: 100.0}
+""" % (mech, mech))
+    res = app.run(str(cfg), n_outputs=100, results_dir=str(tmp_path / "out"))
+    assert len(res) == 3 and all(r["status"] >= 0 for r in res)
+    g = __import__("json").load(open(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "reference_goldens.json")))["slide_trajectory"]
+    T = res[0]["temperature"]
+    for i, v in g["T"].items():
+        assert abs(T[int(i)] / v - 1) < TRAJ_TOL
+    assert abs(res[1]["temperature"][0] - 1200.0) < 5.0 and res[1]["ignition_delay"] < res[0]["ignition_delay"]
+    h = H5Min(res[0]["file"]).root
+    assert sorted(h) == ["Mass fractions", "Temperature", "Time"]
+    assert np.array_equal(h["Temperature"]["Temperature"]["data"], T)
+    assert h["Mass fractions"]["H2"]["attrs"] == {"Name": "Y_H2", "Notation": "Y_H2", "Unit": "-"}
+    h3 = H5Min(res[2]["file"]).root
+    assert sorted(h3) == ["Mass fractions", "Time"]          # Base registers no temperature for the T-fixed types

@@ -1,0 +1,52 @@
+"""Results writer: layout of the reference's HDF5Writer (src/results/hdf5_writer.cpp:136-217, base.cpp:123-142,
+:210-218), checked with the structural reader of tests/h5_min_reader.py."""
+import numpy as np
+import pytest
+
+from h5_min_reader import H5Min
+
+
+def test_single_reactor_layout(ctb, chem, tmp_path):
+    from chemtools_b200.results import write_case_hdf5
+    ch = chem("gri30")
+    n_out = 100
+    rng = np.random.default_rng(0)
+    res = dict(time=np.arange(1, n_out + 1) * 1e-5, temperature=1000 + rng.random(n_out), species=ch.species_names,
+               mass_fractions=rng.random((n_out, ch.n_species)))
+    f = tmp_path / "test.h5"
+    write_case_hdf5(str(f), res)
+    h = H5Min(str(f)).root
+    assert sorted(h) == ["Mass fractions", "Temperature", "Time"]          # scripts/results/demo.py:7-9
+    assert np.array_equal(h["Time"]["Time"]["data"], res["time"])
+    assert h["Time"]["Time"]["attrs"] == {"Name": "Time", "Notation": "t", "Unit": "s"}
+    assert np.array_equal(h["Temperature"]["Temperature"]["data"], res["temperature"])
+    assert h["Temperature"]["Temperature"]["attrs"] == {"Name": "Temperature", "Notation": "T", "Unit": "K"}
+    mf = h["Mass fractions"]
+    assert sorted(mf) == sorted(ch.species_names) and len(mf) == 53      # > 32 entries in one group
+    for k, sp in enumerate(ch.species_names):
+        assert np.array_equal(mf[sp]["data"], res["mass_fractions"][:, k])
+        assert mf[sp]["attrs"] == {"Name": "Y_" + sp, "Notation": "Y_" + sp, "Unit": "-"}
+
+
+def test_batch_layout_and_many_entries(ctb, tmp_path):
+    from chemtools_b200.results import HDF5Writer, write_batch_hdf5
+    rng = np.random.default_rng(1)
+    n, n_out, K = 5, 7, 3
+    traj = rng.random((n, n_out, K + 1))
+    f = tmp_path / "batch.h5"
+    write_batch_hdf5(str(f), ["A", "B(S)", "C2H6"], np.linspace(0, 1, n_out), traj, tau=rng.random(n), status=[0, 1, -1, 0, 0],
+                     stats=rng.integers(0, 100, (n, 8)))
+    h = H5Min(str(f)).root
+    assert h["Temperature"]["Temperature"]["data"].shape == (n, n_out)
+    assert np.array_equal(h["Mass fractions"]["B(S)"]["data"], traj[:, :, 2])
+    assert np.array_equal(h["Solver"]["Status"]["data"], [0, 1, -1, 0, 0])
+    # a group with more entries than one symbol-table node holds (2K = 64): several SNODs under one B-tree node
+    w = HDF5Writer()
+    for i in range(150):
+        w.add("/big/d%03d" % i, np.full(2, float(i)), "n", "n", "-")
+    w.add("/scalar/x", np.float64(3.5))
+    w.write(str(tmp_path / "big.h5"))
+    h = H5Min(str(tmp_path / "big.h5")).root
+    assert len(h["big"]) == 150 and h["big"]["d149"]["data"][1] == 149.0 and h["scalar"]["x"]["data"] == 3.5
+    with pytest.raises(ctb.reactors.CtError):
+        w.add("/big/d000", np.zeros(2))      # duplicate object
