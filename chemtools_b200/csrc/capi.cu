@@ -68,7 +68,7 @@ MechDesc make_desc(const CompiledMech& C) {
   d.o_eff_sp = o.eff_sp; d.o_ftype = o.ftype; d.o_stoich = o.stoich; d.o_ent = o.ent; d.o_pstart = o.pstart; d.o_pnplus = o.pnplus;
   d.o_lpp = o.lpp; d.o_spp = o.spp; d.n_pieces = o.n_pieces;
   d.blob_bytes = o.total;
-  static_assert(sizeof(MechDesc) <= CT_HDR_BYTES, "MechDesc must fit the shared header");
+  static_assert(sizeof(MechDesc) <= CT_GANG_OFF, "MechDesc must fit the shared header");
   return d;
 }
 
@@ -116,8 +116,9 @@ struct ct_batch {
   int64_t n = 0;
   double rtol = 1e-8, atol = 1e-14, t_stop = 1e-3;
   int64_t mxstep = 500;
-  int max_order = 5, jac_mode = CT_JAC_ANALYTIC, ign_mode = 1, linsol = LINSOL_LU;
+  int max_order = 5, jac_mode = CT_JAC_ANALYTIC, ign_mode = 1, linsol = LINSOL_INVERSE;
   double ign_value = 400.0, jac_clip = 1.0;
+  int gang = 1;
   bool have_ic = false, fresh = true, roberts = false;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -164,7 +165,7 @@ BatchArgs make_args(ct_batch* b) {
   BatchArgs a{};
   a.rt = b->roberts ? RT_ROBERTS : b->rt;
   a.N = b->N; a.jac_mode = b->jac_mode; a.max_order = b->max_order; a.ign_mode = b->ign_mode; a.fresh = b->fresh ? 1 : 0;
-  a.n_out = 0; a.n = b->n; a.mxstep = b->mxstep; a.linsol = b->linsol; a.jac_clip = b->jac_clip;
+  a.n_out = 0; a.n = b->n; a.mxstep = b->mxstep; a.linsol = b->linsol; a.jac_clip = b->jac_clip; a.gang = b->gang;
   a.T0 = b->pT0; a.p0 = b->pp0; a.rho0 = b->rho0.p;
   a.nt = b->nt; a.tab_t = b->tab_t.p; a.tab_T = b->tab_T.p; a.tab_p = b->tab_p.p;
   a.rtol = b->rtol; a.atol = b->atol; a.atol_vec = b->atol_vec.n ? b->atol_vec.p : nullptr;
@@ -489,6 +490,11 @@ int ct_batch_set_jacobian(ct_batch* b, int mode) {
 int ct_batch_set_linear_solver(ct_batch* b, int mode) {
   if (!b || (mode != LINSOL_LU && mode != LINSOL_INVERSE)) return fail(CT_ERR_INVALID, "bad linear solver mode");
   b->linsol = mode;
+  return 0;
+}
+int ct_batch_set_phase_alignment(ct_batch* b, int on) {
+  if (!b) return fail(CT_ERR_INVALID, "null batch");
+  b->gang = on ? 1 : 0;
   return 0;
 }
 int ct_batch_set_jacobian_clip(ct_batch* b, double thr) {

@@ -184,6 +184,9 @@ class ReactorBatch:
     def SetJacobianClip(self, thr):
         check(lib().ct_batch_set_jacobian_clip(self._h, float(thr)))
 
+    def SetPhaseAlignment(self, on):
+        check(lib().ct_batch_set_phase_alignment(self._h, 1 if on else 0))
+
     def SetIgnition(self, mode, value):
         check(lib().ct_batch_set_ignition(self._h, {"absolute": 0, "rise": 1}.get(mode, mode), float(value)))
 

@@ -126,14 +126,16 @@ int ct_batch_set_max_steps(ct_batch*, int64_t mxstep);
 /* Solver::SetMaxOrder (interface.hpp:83), 1..5 */
 int ct_batch_set_max_order(ct_batch*, int q);
 int ct_batch_set_jacobian(ct_batch*, int mode);
-/* Newton linear algebra: CT_LINSOL_LU (default) = LU + triangular solves (what SUNLinSol_Dense does,
- * interface.cpp:714-721); CT_LINSOL_INVERSE = Gauss-Jordan inverse of I - gamma*J once per setup, each solve one
- * mat-vec: ~7 % faster on config 2 but measurably less robust at tight tolerances (the inverse's rounding error
- * pollutes the local error estimate) */
+/* Newton linear algebra: CT_LINSOL_LU = LU + triangular solves (what SUNLinSol_Dense does, interface.cpp:714-721);
+ * CT_LINSOL_INVERSE (default) = Gauss-Jordan inverse of the error-weight-equilibrated I - gamma*J once per setup, each
+ * Newton solve one mat-vec (no 108-step serial dependency): 15-20 % faster on config 2, same step counts */
 int ct_batch_set_linear_solver(ct_batch*, int mode);
 /* analytic Jacobian: the column of species j is zeroed iff y_j * ewt_j < -thr (Cantera clips negative mass
  * fractions, so the right-hand side does not depend on them); default 1 */
 int ct_batch_set_jacobian_clip(ct_batch*, double thr);
+/* scheduling only (results are unaffected): align the warps of a CTA in front of every Newton residual so that they
+ * share instruction fetches (the fused kernel is instruction-cache bound); default on */
+int ct_batch_set_phase_alignment(ct_batch*, int on);
 /* ignition monitor: mode 0 = first crossing of T >= value (reference test: 1756 K, tests/src/reactor.cpp:130),
  * mode 1 = T >= T0 + value (default, value = 400 K); located on the integrator's dense output */
 int ct_batch_set_ignition(ct_batch*, int mode, double value);
