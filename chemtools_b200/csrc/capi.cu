@@ -68,7 +68,7 @@ MechDesc make_desc(const CompiledMech& C) {
   d.o_eff_sp = o.eff_sp; d.o_ftype = o.ftype; d.o_stoich = o.stoich; d.o_ent = o.ent; d.o_pstart = o.pstart; d.o_pnplus = o.pnplus;
   d.o_lpp = o.lpp; d.o_spp = o.spp; d.n_pieces = o.n_pieces;
   d.blob_bytes = o.total;
-  static_assert(sizeof(MechDesc) <= CT_GANG_OFF, "MechDesc must fit the shared header");
+  static_assert(sizeof(MechDesc) <= CT_GANG_OFF && CT_POOL_OFF + 16 <= CT_HDR_BYTES, "MechDesc must fit the shared header");
   return d;
 }
 
@@ -118,7 +118,7 @@ struct ct_batch {
   int64_t mxstep = 500;
   int max_order = 5, jac_mode = CT_JAC_ANALYTIC, ign_mode = 1, linsol = LINSOL_INVERSE;
   double ign_value = 400.0, jac_clip = 1.0;
-  int gang = 1;
+  int gang = 1, pool_enabled = 1, pool_n = 0, pool_warps = 12, gang_groups = 1, gang_sleep_ns = 200, gang_max_polls = 0;
   bool have_ic = false, fresh = true, roberts = false;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -155,6 +155,19 @@ int configure_launch(ct_batch* b) {
   w = std::min(w, 16);
   b->wpb = w;
   b->smem = fixed + (size_t)w * slab;
+  b->pool_n = 0;
+  // pool mode: Newton matrix out of the per-warp slab (shared work slabs + inverse in global scratch) when the classic
+  // layout leaves fewer than 10 warps per SM; needs the explicit-inverse solver
+  if (b->pool_enabled && b->mech && b->linsol == LINSOL_INVERSE && w < 10) {
+    const size_t slabW = (size_t)make_layout(b->N, d.R, false).doubles * sizeof(double);
+    const size_t slabM = pool_slab_bytes(b->N);
+    const int pw = std::max(8, std::min(16, b->pool_warps));
+    if (fixed + 16 + (size_t)pw * slabW + 3 * slabM <= avail) {
+      const int pn = (int)std::min<size_t>(16, (avail - fixed - 16 - (size_t)pw * slabW) / slabM);
+      b->wpb = pw; b->pool_n = pn; w = pw;
+      b->smem = ((fixed + (size_t)pw * slabW + 15) & ~(size_t)15) + (size_t)pn * slabM;
+    }
+  }
   // persistent: one CTA per SM, never more warps than reactors
   int64_t need = (b->n + w - 1) / w;
   b->grid = (int)std::max<int64_t>(1, std::min<int64_t>(di.sms, need));
@@ -165,7 +178,7 @@ BatchArgs make_args(ct_batch* b) {
   BatchArgs a{};
   a.rt = b->roberts ? RT_ROBERTS : b->rt;
   a.N = b->N; a.jac_mode = b->jac_mode; a.max_order = b->max_order; a.ign_mode = b->ign_mode; a.fresh = b->fresh ? 1 : 0;
-  a.n_out = 0; a.n = b->n; a.mxstep = b->mxstep; a.linsol = b->linsol; a.jac_clip = b->jac_clip; a.gang = b->gang;
+  a.n_out = 0; a.n = b->n; a.mxstep = b->mxstep; a.linsol = b->linsol; a.jac_clip = b->jac_clip; a.gang = b->gang; a.pool_n = b->pool_n; a.gang_groups = b->gang_groups; a.gang_sleep_ns = b->gang_sleep_ns; a.gang_max_polls = b->gang_max_polls;
   a.T0 = b->pT0; a.p0 = b->pp0; a.rho0 = b->rho0.p;
   a.nt = b->nt; a.tab_t = b->tab_t.p; a.tab_T = b->tab_T.p; a.tab_p = b->tab_p.p;
   a.rtol = b->rtol; a.atol = b->atol; a.atol_vec = b->atol_vec.n ? b->atol_vec.p : nullptr;
@@ -201,6 +214,9 @@ int launch_integrate(ct_batch* b, BatchArgs& a) {
   if (b->wpb <= 8) {
     if (int r = set_smem(k_integrate<256>, b->smem)) return r;
     k_integrate<256><<<b->grid, b->wpb * 32, b->smem, b->stream>>>(d, blob, a);
+  } else if (b->wpb <= 12) {
+    if (int r = set_smem(k_integrate<384>, b->smem)) return r;
+    k_integrate<384><<<b->grid, b->wpb * 32, b->smem, b->stream>>>(d, blob, a);
   } else {
     if (int r = set_smem(k_integrate<512>, b->smem)) return r;
     k_integrate<512><<<b->grid, b->wpb * 32, b->smem, b->stream>>>(d, blob, a);
@@ -492,9 +508,27 @@ int ct_batch_set_linear_solver(ct_batch* b, int mode) {
   b->linsol = mode;
   return 0;
 }
+int ct_batch_set_matrix_pool(ct_batch* b, int on, int warps_per_sm) {
+  if (!b) return fail(CT_ERR_INVALID, "null batch");
+  b->pool_enabled = on ? 1 : 0;
+  if (warps_per_sm > 0) b->pool_warps = warps_per_sm;
+  return 0;
+}
 int ct_batch_set_phase_alignment(ct_batch* b, int on) {
   if (!b) return fail(CT_ERR_INVALID, "null batch");
   b->gang = on ? 1 : 0;
+  if (on > 1) b->gang_groups = 2;  // two alignment groups (even / odd warps)
+  else b->gang_groups = 1;
+  return 0;
+}
+int ct_batch_set_alignment_poll_ns(ct_batch* b, int ns) {
+  if (!b || ns < 0) return fail(CT_ERR_INVALID, "bad argument");
+  b->gang_sleep_ns = ns;
+  return 0;
+}
+int ct_batch_set_alignment_max_polls(ct_batch* b, int polls) {
+  if (!b || polls < 0) return fail(CT_ERR_INVALID, "bad argument");
+  b->gang_max_polls = polls;
   return 0;
 }
 int ct_batch_set_jacobian_clip(ct_batch* b, double thr) {
@@ -610,7 +644,12 @@ int ct_batch_warps_per_sm(const ct_batch* b) { return b ? b->wpb : 0; }
 // ---------------------------------------------------------------- stand-alone kernels
 static int standalone_cfg(ct_batch* b, int* wpb, int* grid, size_t* smem, bool need_scratch) {
   if (int r = configure_launch(b)) return r;
-  *wpb = std::min(b->wpb, 8);
+  {
+    DeviceInfo di0;
+    if (int r = device_info(di0)) return r;
+    const size_t slab_c = (size_t)make_layout(b->N, b->mech->desc.R).doubles * sizeof(double);
+    *wpb = (int)std::min<size_t>(8, ((size_t)di0.max_smem_optin - CT_HDR_BYTES - b->mech->desc.blob_bytes) / slab_c);
+  }
   const WarpLayout L = make_layout(b->N, b->mech->desc.R);
   *smem = CT_HDR_BYTES + b->mech->desc.blob_bytes + (size_t)*wpb * L.doubles * sizeof(double);
   DeviceInfo di;
@@ -635,6 +674,7 @@ int ct_rhs_eval(ct_batch* b, const double* states, const double* times, double* 
   if (times) { CT_CUDA(b->tmp_t.alloc(b->n)); CT_CUDA(cudaMemcpyAsync(b->tmp_t.p, times, b->n * sizeof(double), cudaMemcpyHostToDevice, b->stream)); }
   if (qf) { CT_CUDA(b->tmp_qf.alloc((size_t)b->n * R)); CT_CUDA(b->tmp_qr.alloc((size_t)b->n * R)); }
   BatchArgs a = make_args(b);
+  a.pool_n = 0;
   if (int r = set_smem(k_rhs, smem)) return r;
   k_rhs<<<grid, wpb * 32, smem, b->stream>>>(b->mech->desc, blob, a, b->tmp_in.p, times ? b->tmp_t.p : nullptr, b->tmp_out.p,
                                              b->tmp_w.p, qf ? b->tmp_qf.p : nullptr, qf ? b->tmp_qr.p : nullptr, perm);
@@ -662,6 +702,7 @@ int ct_rhs_time(ct_batch* b, const double* states, int reps, double* ms) {
   CT_CUDA(cudaMemcpy(b->tmp_in.p, states, nN * sizeof(double), cudaMemcpyHostToDevice));
   if (!b->ev0) { CT_CUDA(cudaEventCreate(&b->ev0)); CT_CUDA(cudaEventCreate(&b->ev1)); }
   BatchArgs a = make_args(b);
+  a.pool_n = 0;
   if (int r = set_smem(k_rhs, smem)) return r;
   for (int w = 0; w < 3; ++w) k_rhs<<<grid, wpb * 32, smem, b->stream>>>(b->mech->desc, blob, a, b->tmp_in.p, nullptr, b->tmp_out.p, b->tmp_w.p, nullptr, nullptr, perm);
   CT_CUDA(cudaEventRecord(b->ev0, b->stream));
@@ -683,6 +724,7 @@ static int jac_launch(ct_batch* b, int mode, const double* d_states, const doubl
   if (int r = b->mech->on_device(&blob, nullptr)) return r;
   if (!b->ev0) { CT_CUDA(cudaEventCreate(&b->ev0)); CT_CUDA(cudaEventCreate(&b->ev1)); }
   BatchArgs a = make_args(b);
+  a.pool_n = 0;
   a.jac_mode = mode;
   if (int r = set_smem(k_jacobian, smem)) return r;
   if (ms) for (int w = 0; w < 2; ++w) k_jacobian<<<grid, wpb * 32, smem, b->stream>>>(b->mech->desc, blob, a, d_states, d_times, 1e-8, d_J);

@@ -185,7 +185,16 @@ class ReactorBatch:
         check(lib().ct_batch_set_jacobian_clip(self._h, float(thr)))
 
     def SetPhaseAlignment(self, on):
-        check(lib().ct_batch_set_phase_alignment(self._h, 1 if on else 0))
+        check(lib().ct_batch_set_phase_alignment(self._h, int(on)))
+
+    def SetAlignmentPollNs(self, ns):
+        check(lib().ct_batch_set_alignment_poll_ns(self._h, int(ns)))
+
+    def SetAlignmentMaxPolls(self, n):
+        check(lib().ct_batch_set_alignment_max_polls(self._h, int(n)))
+
+    def SetMatrixPool(self, on, warps_per_sm=0):
+        check(lib().ct_batch_set_matrix_pool(self._h, 1 if on else 0, int(warps_per_sm)))
 
     def SetIgnition(self, mode, value):
         check(lib().ct_batch_set_ignition(self._h, {"absolute": 0, "rise": 1}.get(mode, mode), float(value)))

@@ -135,7 +135,13 @@ int ct_batch_set_linear_solver(ct_batch*, int mode);
 int ct_batch_set_jacobian_clip(ct_batch*, double thr);
 /* scheduling only (results are unaffected): align the warps of a CTA in front of every Newton residual so that they
  * share instruction fetches (the fused kernel is instruction-cache bound); default on */
-int ct_batch_set_phase_alignment(ct_batch*, int on);
+int ct_batch_set_phase_alignment(ct_batch*, int on); /* 0 off, 1 one group per CTA (default), 2 two groups (even/odd warps) */
+int ct_batch_set_alignment_poll_ns(ct_batch*, int ns); /* sleep between polls of the alignment barrier, default 200 */
+int ct_batch_set_alignment_max_polls(ct_batch*, int polls); /* bounded wait: give up after that many polls; 0 = unbounded */
+/* scheduling only: keep the N x N Newton matrix out of the per-warp shared-memory slab (shared pool of work slabs for
+ * Jacobian assembly + inversion, inverse parked in L2-resident global scratch) so that warps_per_sm (default 12)
+ * instead of 6 warps fit one SM for GRI-3.0; applies with CT_LINSOL_INVERSE; default on */
+int ct_batch_set_matrix_pool(ct_batch*, int on, int warps_per_sm);
 /* ignition monitor: mode 0 = first crossing of T >= value (reference test: 1756 K, tests/src/reactor.cpp:130),
  * mode 1 = T >= T0 + value (default, value = 400 K); located on the integrator's dense output */
 int ct_batch_set_ignition(ct_batch*, int mode, double value);

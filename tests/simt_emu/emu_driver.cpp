@@ -27,7 +27,7 @@ MechDesc desc_of(const CompiledMech& C) {
   d.o_eff_sp = o.eff_sp; d.o_ftype = o.ftype; d.o_stoich = o.stoich; d.o_ent = o.ent; d.o_pstart = o.pstart; d.o_pnplus = o.pnplus;
   d.o_lpp = o.lpp; d.o_spp = o.spp; d.n_pieces = o.n_pieces;
   d.blob_bytes = o.total;
-  static_assert(sizeof(MechDesc) <= CT_GANG_OFF, "MechDesc must fit the shared header");
+  static_assert(sizeof(MechDesc) <= CT_GANG_OFF && CT_POOL_OFF + 16 <= CT_HDR_BYTES, "MechDesc must fit the shared header");
   return d;
 }
 }  // namespace
@@ -92,7 +92,7 @@ int emu_lu_solve(int N, long long n, const double* A, const double* b, double* x
 int emu_integrate(void* mv, int rt, long long n, const double* T0, const double* p0, const double* Y0, double rtol, double atol,
                   double t_end, long long mxstep, int jac_mode, int ign_mode, double ign_value, int n_out, int n_calls,
                   int nt, const double* tab_t, const double* tab_T, const double* tab_p,
-                  double* traj, double* state, double* tau, long long* stats, int* status, int warps, int linsol, double jac_clip) {
+                  double* traj, double* state, double* tau, long long* stats, int* status, int warps, int linsol, double jac_clip, int pool_n) {
   EmuMech* m = (EmuMech*)mv;
   const int N = rt <= 1 ? m->C.K + 1 : m->C.K;
   std::vector<double> rho0(n), tcur(n);
@@ -105,10 +105,10 @@ int emu_integrate(void* mv, int rt, long long n, const double* T0, const double*
   a.mxstep = mxstep; a.T0 = T0; a.p0 = p0; a.rho0 = rho0.data(); a.rtol = rtol; a.atol = atol; a.t_target = t_end; a.t_stop = t_end;
   a.nt = nt; a.tab_t = tab_t; a.tab_T = tab_T; a.tab_p = tab_p;
   a.ign_value = ign_value; a.state = state; a.traj = traj; a.tau = tau; a.tcur = tcur.data(); a.stats = stats; a.status = status;
-  a.counter = &counter; a.scratch = scratch.data(); a.linsol = linsol; a.jac_clip = jac_clip; a.gang = 1;
+  a.counter = &counter; a.scratch = scratch.data(); a.linsol = linsol; a.jac_clip = jac_clip; a.gang = 1; a.pool_n = pool_n;
   a.save_stride = CT_LMAX * CT_NP + CT_SAVE_SCALARS;
-  const WarpLayout L = make_layout(N, m->d.R);
-  const size_t smem = CT_HDR_BYTES + m->d.blob_bytes + (size_t)warps * L.doubles * 8;
+  const WarpLayout L = make_layout(N, m->d.R, pool_n == 0);
+  const size_t smem = ((CT_HDR_BYTES + m->d.blob_bytes + (size_t)warps * L.doubles * 8 + 15) & ~(size_t)15) + (size_t)pool_n * pool_slab_bytes(N);
   std::vector<double> save;
   for (long long i = 0; i < n; ++i) status[i] = 0;
   if (n_calls <= 1) {

@@ -26,7 +26,7 @@ def emu():
         os.path.join(ROOT, "chemtools_b200", "csrc", f) for f in ("kernels.cuh", "cti_parser.cpp", "mech_compile.cpp", "mechanism.hpp")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-D__align__(x)=alignas(x)", "-o", so,
-                               srcs[0], srcs[4], srcs[5]])
+                               srcs[0], srcs[3], srcs[4]])
     L = C.CDLL(so)
     L.emu_mech_load.restype = C.c_void_p
     L.emu_mech_load.argtypes = [C.c_char_p, C.c_char_p]
@@ -36,7 +36,7 @@ def emu():
     L.emu_lu_solve.argtypes = [C.c_int, C.c_longlong, dp, dp, dp, ip, C.c_int]
     L.emu_integrate.argtypes = [C.c_void_p, C.c_int, C.c_longlong, dp, dp, dp, C.c_double, C.c_double, C.c_double, C.c_longlong,
                                 C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, lp, ip, C.c_int,
-                                C.c_int, C.c_double]
+                                C.c_int, C.c_double, C.c_int]
     L.emu_roberts.argtypes = [C.c_int, dp, C.c_double, dp, dp, lp]
     return L
 
@@ -55,7 +55,7 @@ def emech(emu, ctb):
 
 
 def _integrate(emu, h, om, rt, T0, p0, Y, rtol, atol, t_end, jac=1, linsol=0, n_out=0, n_calls=1, warps=1, mxstep=20000,
-               ign=(1, 400.0)):
+               ign=(1, 400.0), pool_n=0):
     n = len(T0)
     N = om.K + 1 if rt <= 1 else om.K
     T0 = np.ascontiguousarray(T0, dtype=float); p0 = np.ascontiguousarray(p0, dtype=float); Y = np.ascontiguousarray(Y, dtype=float)
@@ -63,7 +63,7 @@ def _integrate(emu, h, om, rt, T0, p0, Y, rtol, atol, t_end, jac=1, linsol=0, n_
     traj = np.zeros((n, nt, N)) if nt else None
     state = np.zeros((n, N)); tau = np.zeros(n); stats = np.zeros((n, 8), dtype=np.int64); status = np.zeros(n, dtype=np.int32)
     emu.emu_integrate(h, rt, n, P(T0), P(p0), P(Y), rtol, atol, t_end, mxstep, jac, ign[0], ign[1], n_out, n_calls, 0, None, None, None,
-                      P(traj), P(state), P(tau), stats.ctypes.data_as(lp), status.ctypes.data_as(ip), warps, linsol, 1.0)
+                      P(traj), P(state), P(tau), stats.ctypes.data_as(lp), status.ctypes.data_as(ip), warps, linsol, 1.0, pool_n)
     return dict(state=state, tau=tau, stats=stats, status=status, traj=traj)
 
 
@@ -167,3 +167,9 @@ def test_work_queue_resume_and_failure_codes(emu, emech, omech):
     assert np.abs(many["state"][:, 0] / ref["state"][:, 0] - 1).max() < 1e-4
     few = _integrate(emu, h, om, 1, T0, p0, Y, 1e-8, 1e-14, 2e-4, mxstep=20)
     assert np.all(few["status"] == -1)
+    # pool mode: Newton matrix in a shared pool of work slabs (fewer slabs than warps), inverse in global scratch
+    pooled = _integrate(emu, h, om, 1, T0, p0, Y, 1e-8, 1e-14, 2e-4, warps=3, linsol=1, pool_n=2)
+    assert np.all(pooled["status"] >= 0)
+    assert np.abs(pooled["state"][:, 0] / ref["state"][:, 0] - 1).max() < 1e-4
+    inv = _integrate(emu, h, om, 1, T0, p0, Y, 1e-8, 1e-14, 2e-4, warps=2, linsol=1)
+    assert np.abs(inv["state"][:, 0] / pooled["state"][:, 0] - 1).max() < 1e-6

@@ -1,4 +1,4 @@
-"""A/B probe of scheduling / linear-algebra options on config 2 (development aid)."""
+"""A/B probe of scheduling options on config 2 (development aid)."""
 import sys, os, json
 import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
@@ -7,12 +7,14 @@ from chemtools_b200 import workloads as W
 chem = ctb.ThermoKinetics(ctb.mechanism_path("gri30"))
 mech, rt, T0, p0, X, t_end, extra = W.config2(chem, int(os.environ.get("SIDE", "64")))
 Y = chem.mass_fractions(X)
+cases = [dict(w=12), dict(w=12, polls=2), dict(w=12, polls=5), dict(w=12, polls=10), dict(w=12, polls=20), dict(w=12, polls=40), dict(w=12, polls=10, ns=100)]
+last = None
 for rep in range(2):
-    for gang in (1, 0):
-        for linsol in ("lu", "inverse"):
-            b = ctb.ReactorBatch(rt, chem, T0, p0, Y, 1e-8, 1e-14, t_end, max_num_steps=50000)
-            b.SetLinearSolver(linsol); b.SetPhaseAlignment(gang)
-            code = b.Integrate(t_end)
-            st = b.Statistics()
-            print(json.dumps(dict(rep=rep, gang=gang, linsol=linsol, code=int(code), kernel_ms=round(b.LastKernelMs(), 2), reactors_per_s=round(len(T0) / b.LastKernelMs() * 1e3),
-                                  nst_mean=float(st[:, 0].mean()), nfe_mean=float(st[:, 1].mean()))), flush=True)
+    for c in cases:
+        b = ctb.ReactorBatch(rt, chem, T0, p0, Y, 1e-8, 1e-14, t_end, max_num_steps=50000)
+        b.SetPhaseAlignment(c.get("gang", 1)); b.SetMatrixPool(1, c.get("w", 0)); b.SetAlignmentPollNs(c.get("ns", 200)); b.SetAlignmentMaxPolls(c.get("polls", 0))
+        if c.get("order") and last is not None:
+            b.SetOrder(np.argsort(-last[:, 1], kind="stable").astype(np.int32))
+        code = b.Integrate(t_end)
+        st = b.Statistics(); last = st
+        print(json.dumps(dict(rep=rep, **c, code=int(code), wpb=b.WarpsPerSM(), kernel_ms=round(b.LastKernelMs(), 2), reactors_per_s=round(len(T0) / b.LastKernelMs() * 1e3))), flush=True)
