@@ -309,7 +309,8 @@ def main():
             "metric": "GRI-3.0 reactors integrated to 1 ms per sec", "value": world * n * args.steps / (ms_total * 1e-3), "unit": "reactors/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["desc"], "reactors_per_gpu_per_step": n, "rtol": RTOL, "atol": ATOL, "jacobian": "analytic",
+            "config": {"workload": wl["desc"], "reactors_per_gpu_per_step": n, "rtol": RTOL, "atol": ATOL, "jacobian": "analytic", "newton_solver": "equilibrated Gauss-Jordan inverse + mat-vec",
+                       "scheduling": "persistent CTAs, atomic work queue (hottest first), phase-aligned warps, Newton matrices in a shared pool",
                        "l2": "256 MiB buffer rewritten between iterations (L2 flush)", "parallelism": "independent ensembles x%d, no collective" % world,
                        "warps_per_sm": b.WarpsPerSM()},
             "e2e": {"value": world * n * args.steps / (e2e_ms * 1e-3), "unit": "reactors/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -117,7 +117,7 @@ struct ct_batch {
   double rtol = 1e-8, atol = 1e-14, t_stop = 1e-3;
   int64_t mxstep = 500;
   int max_order = 5, jac_mode = CT_JAC_ANALYTIC, ign_mode = 1, linsol = LINSOL_INVERSE;
-  double ign_value = 400.0, jac_clip = 1.0;
+  double ign_value = 400.0, jac_clip = 10.0;
   int gang = 1, pool_enabled = 1, pool_n = 0, pool_warps = 12, gang_groups = 1, gang_sleep_ns = 200, gang_max_polls = 0;
   bool have_ic = false, fresh = true, roberts = false;
   cudaStream_t stream = nullptr;

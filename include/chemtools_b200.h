@@ -130,8 +130,12 @@ int ct_batch_set_jacobian(ct_batch*, int mode);
  * CT_LINSOL_INVERSE (default) = Gauss-Jordan inverse of the error-weight-equilibrated I - gamma*J once per setup, each
  * Newton solve one mat-vec (no 108-step serial dependency): 15-20 % faster on config 2, same step counts */
 int ct_batch_set_linear_solver(ct_batch*, int mode);
-/* analytic Jacobian: the column of species j is zeroed iff y_j * ewt_j < -thr (Cantera clips negative mass
- * fractions, so the right-hand side does not depend on them); default 1 */
+/* analytic Jacobian: the column of species j is zeroed iff y_j * ewt_j < -thr.  Cantera clips negative mass
+ * fractions, so the right-hand side does not depend on them (the true column is zero, as CVODE's difference quotients
+ * see it); but a species hovering a few atol below zero with positive production is about to re-enter the unclipped
+ * branch, and a zero column then makes modified Newton overshoot across the kink every step (period-2 sawtooth, step
+ * size pinned at ~atol/production: 6e4..2e5 steps per ms for burnt lean CH4, in the reference algorithm too).
+ * Default 10: measured optimum on the config-5 slice (max steps 61285 -> 4842, 4x throughput); 0 = CVODE-like */
 int ct_batch_set_jacobian_clip(ct_batch*, double thr);
 /* scheduling only (results are unaffected): align the warps of a CTA in front of every Newton residual so that they
  * share instruction fetches (the fused kernel is instruction-cache bound); default on */
