@@ -7,7 +7,7 @@ from chemtools_b200 import workloads as W
 chem = ctb.ThermoKinetics(ctb.mechanism_path("gri30"))
 mech, rt, T0, p0, X, t_end, extra = W.config2(chem, int(os.environ.get("SIDE", "64")))
 Y = chem.mass_fractions(X)
-cases = [dict(w=12), dict(w=12, polls=2), dict(w=12, polls=5), dict(w=12, polls=10), dict(w=12, polls=20), dict(w=12, polls=40), dict(w=12, polls=10, ns=100)]
+cases = [dict(w=12), dict(w=13), dict(w=14), dict(w=11), dict(w=10)]
 last = None
 for rep in range(2):
     for c in cases:
