@@ -87,6 +87,9 @@ def lib():
         "ct_batch_set_jacobian_clip": (i32, [vp, dbl]),
         "ct_batch_set_phase_alignment": (i32, [vp, i32]),
         "ct_batch_set_matrix_pool": (i32, [vp, i32, i32]),
+        "ct_batch_set_time_slicing": (i32, [vp, i32]),
+        "ct_batch_set_timeline": (i32, [vp, i32]),
+        "ct_batch_get_timeline": (i32, [vp, vp]),
         "ct_batch_set_alignment_poll_ns": (i32, [vp, i32]),
         "ct_batch_set_alignment_max_polls": (i32, [vp, i32]),
         "ct_batch_set_tp_table": (i32, [vp, i32, dp, dp, dp]),

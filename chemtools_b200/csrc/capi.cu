@@ -126,6 +126,10 @@ struct ct_batch {
   DevBuf<long long> stats;
   DevBuf<int> status, order;
   DevBuf<unsigned long long> counter;
+  DevBuf<long long> timeline; int timeline_on = 0;
+  // time slicing (see BatchArgs): ring of reactor ids, per-reactor scratch
+  DevBuf<int> ring, yielded; DevBuf<unsigned long long> ring_seq, qctl;
+  int slice_steps = 64, ring_cap = 0; bool sliced = false;
   const double *pT0 = nullptr, *pp0 = nullptr, *pY0 = nullptr;  // owned or borrowed device pointers
   int nt = 0;
   bool have_order = false;
@@ -133,7 +137,7 @@ struct ct_batch {
   int wpb = 0, grid = 0;
   size_t smem = 0;
   double last_ms = 0.0;
-  int64_t launches = 0;
+  int64_t launches = 0, aux_launches = 0;  // solver kernels / k_init + k_ring_init
   ~ct_batch() {
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -171,6 +175,10 @@ int configure_launch(ct_batch* b) {
   // persistent: one CTA per SM, never more warps than reactors
   int64_t need = (b->n + w - 1) / w;
   b->grid = (int)std::max<int64_t>(1, std::min<int64_t>(di.sms, need));
+  // time slicing needs the reactor-indexed scratch (49 KB per GRI-3.0 reactor): only while that stays below 4 GiB and
+  // the batch is more than one wave of warps (otherwise nothing ever waits for a warp)
+  b->sliced = b->slice_steps > 0 && b->pool_n > 0 && b->n > (int64_t)b->grid * w &&
+              (double)b->n * (double)warp_scratch_doubles(b->N, d.R) * 8.0 <= 4.0 * 1024 * 1024 * 1024;
   return 0;
 }
 
@@ -186,6 +194,11 @@ BatchArgs make_args(ct_batch* b) {
   a.state = b->state.p; a.save = nullptr; a.save_stride = CT_LMAX * CT_NP + CT_SAVE_SCALARS; a.traj = nullptr;
   a.tau = b->tau.p; a.tcur = b->tcur.p; a.stats = b->stats.p; a.status = b->status.p; a.counter = b->counter.p;
   a.scratch = b->scratch.p; a.order = b->have_order ? b->order.p : nullptr;
+  a.timeline = b->timeline_on ? b->timeline.p : nullptr;
+  if (b->sliced) {
+    a.slice_steps = b->slice_steps; a.ring_cap = b->ring_cap; a.ring = b->ring.p; a.ring_seq = b->ring_seq.p; a.qctl = b->qctl.p;
+    a.yielded = b->yielded.p; a.save = b->save.p;
+  }
   return a;
 }
 
@@ -198,7 +211,13 @@ int set_smem(Kern k, size_t bytes) {
 int ensure_runtime_buffers(ct_batch* b) {
   if (int r = configure_launch(b)) return r;
   const int R = b->mech ? b->mech->desc.R : 0;
-  CT_CUDA(b->scratch.alloc((size_t)b->grid * b->wpb * warp_scratch_doubles(b->N, R)));
+  const size_t scr = warp_scratch_doubles(b->N, R);
+  CT_CUDA(b->scratch.alloc(std::max((size_t)b->grid * b->wpb * scr, b->sliced ? (size_t)b->n * scr : (size_t)0)));
+  if (b->sliced) {
+    b->ring_cap = (int)std::min<int64_t>(2 * b->n, 2147483647LL);
+    CT_CUDA(b->ring.alloc(b->ring_cap)); CT_CUDA(b->ring_seq.alloc(b->ring_cap)); CT_CUDA(b->qctl.alloc(4)); CT_CUDA(b->yielded.alloc(b->n));
+    CT_CUDA(b->save.alloc((size_t)b->n * (CT_LMAX * CT_NP + CT_SAVE_SCALARS)));
+  }
   CT_CUDA(b->tau.alloc(b->n)); CT_CUDA(b->tcur.alloc(b->n)); CT_CUDA(b->stats.alloc((size_t)b->n * 8));
   CT_CUDA(b->status.alloc(b->n)); CT_CUDA(b->counter.alloc(1));
   if (!b->ev0) { CT_CUDA(cudaEventCreate(&b->ev0)); CT_CUDA(cudaEventCreate(&b->ev1)); }
@@ -210,6 +229,11 @@ int launch_integrate(ct_batch* b, BatchArgs& a) {
   MechDesc d{};
   if (b->mech) { if (int r = b->mech->on_device(&blob, nullptr)) return r; d = b->mech->desc; }
   CT_CUDA(cudaMemsetAsync(b->counter.p, 0, sizeof(unsigned long long), b->stream));
+  if (a.ring) {
+    k_ring_init<<<(a.ring_cap + 255) / 256, 256, 0, b->stream>>>((int)b->n, a.ring_cap, a.order, a.ring, a.ring_seq, a.qctl, a.yielded);
+    CT_CUDA(cudaGetLastError());
+    b->aux_launches += 1;
+  }
   CT_CUDA(cudaEventRecord(b->ev0, b->stream));
   if (b->wpb <= 8) {
     if (int r = set_smem(k_integrate<256>, b->smem)) return r;
@@ -460,6 +484,7 @@ static int finish_ic(ct_batch* b) {
     const int blocks = (int)std::min<int64_t>((b->n + threads - 1) / threads, 4096);
     k_init<<<blocks, threads, 0, b->stream>>>(b->mech->desc, blob, b->rt, b->n, b->pT0, b->pp0, b->pY0, b->state.p, b->rho0.p, b->N);
     CT_CUDA(cudaGetLastError());
+    b->aux_launches += 1;
   }
   b->have_ic = true; b->fresh = true;
   return 0;
@@ -531,6 +556,24 @@ int ct_batch_set_alignment_max_polls(ct_batch* b, int polls) {
   b->gang_max_polls = polls;
   return 0;
 }
+int ct_batch_set_time_slicing(ct_batch* b, int steps) {
+  if (!b || steps < 0) return fail(CT_ERR_INVALID, "bad argument");
+  b->slice_steps = steps;
+  return 0;
+}
+int ct_batch_set_timeline(ct_batch* b, int on) {
+  if (!b) return fail(CT_ERR_INVALID, "null batch");
+  if (on) { CT_CUDA(b->timeline.alloc((size_t)b->n * 3)); CT_CUDA(cudaMemset(b->timeline.p, 0, (size_t)b->n * 3 * sizeof(long long))); }
+  b->timeline_on = on ? 1 : 0;
+  return 0;
+}
+int ct_batch_get_timeline(ct_batch* b, int64_t* out) {
+  if (!b || !out) return fail(CT_ERR_INVALID, "null argument");
+  if (!b->timeline_on || !b->timeline.p) return fail(CT_ERR_INVALID, "timeline recording is off");
+  CT_CUDA(cudaStreamSynchronize(b->stream));
+  CT_CUDA(cudaMemcpy(out, b->timeline.p, (size_t)b->n * 3 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
 int ct_batch_set_jacobian_clip(ct_batch* b, double thr) {
   if (!b || !(thr >= 0.0)) return fail(CT_ERR_INVALID, "bad clip threshold");
   b->jac_clip = thr;
@@ -577,7 +620,7 @@ int ct_batch_integrate(ct_batch* b, double t_target) {
   const bool resumable = t_target < b->t_stop || !b->fresh;
   if (resumable) {
     CT_CUDA(b->save.alloc((size_t)b->n * a.save_stride));
-    a.save = b->save.p;
+    a.save = b->save.p; a.user_save = 1;
   }
   if (b->fresh) CT_CUDA(cudaMemsetAsync(b->status.p, 0, b->n * sizeof(int), b->stream));
   else {
@@ -638,7 +681,7 @@ int ct_batch_get_stats(ct_batch* b, int64_t* out) {
   return 0;
 }
 double ct_batch_last_kernel_ms(const ct_batch* b) { return b ? b->last_ms : 0.0; }
-int64_t ct_batch_launch_count(const ct_batch* b) { return b ? b->launches : 0; }
+int64_t ct_batch_launch_count(const ct_batch* b) { return b ? b->launches + b->aux_launches : 0; }
 int ct_batch_warps_per_sm(const ct_batch* b) { return b ? b->wpb : 0; }
 
 // ---------------------------------------------------------------- stand-alone kernels

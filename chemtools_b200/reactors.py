@@ -196,6 +196,18 @@ class ReactorBatch:
     def SetMatrixPool(self, on, warps_per_sm=0):
         check(lib().ct_batch_set_matrix_pool(self._h, 1 if on else 0, int(warps_per_sm)))
 
+    def SetTimeSlicing(self, steps):
+        check(lib().ct_batch_set_time_slicing(self._h, int(steps)))
+
+    def SetTimeline(self, on=True):
+        check(lib().ct_batch_set_timeline(self._h, 1 if on else 0))
+
+    def Timeline(self):
+        """[n, 3] int64: start ns, end ns (GPU global timer), sm * 64 + warp of every reactor of the last Integrate."""
+        out = np.zeros((self.n, 3), dtype=np.int64)
+        check(lib().ct_batch_get_timeline(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def SetIgnition(self, mode, value):
         check(lib().ct_batch_set_ignition(self._h, {"absolute": 0, "rise": 1}.get(mode, mode), float(value)))
 

@@ -146,6 +146,14 @@ int ct_batch_set_alignment_max_polls(ct_batch*, int polls); /* bounded wait: giv
  * Jacobian assembly + inversion, inverse parked in L2-resident global scratch) so that warps_per_sm (default 12)
  * instead of 6 warps fit one SM for GRI-3.0; applies with CT_LINSOL_INVERSE; default on */
 int ct_batch_set_matrix_pool(ct_batch*, int on, int warps_per_sm);
+/* scheduling only (results are unaffected, the step sequence of every reactor is the uninterrupted one): a warp
+ * integrates a reactor for `steps` steps, parks its stepper state in global memory and queues it again, so that all
+ * reactors of the batch advance together and no warp idles while late starters finish.  Applies with the matrix pool
+ * when the batch exceeds one wave of warps and the reactor-indexed scratch fits 4 GiB.  Default 64; 0 = off */
+int ct_batch_set_time_slicing(ct_batch*, int steps);
+/* scheduling diagnostics: record per reactor [start ns, end ns (GPU global timer), sm * 64 + warp] during Integrate */
+int ct_batch_set_timeline(ct_batch*, int on);
+int ct_batch_get_timeline(ct_batch*, int64_t* out /* n x 3 */);
 /* ignition monitor: mode 0 = first crossing of T >= value (reference test: 1756 K, tests/src/reactor.cpp:130),
  * mode 1 = T >= T0 + value (default, value = 400 K); located on the integrator's dense output */
 int ct_batch_set_ignition(ct_batch*, int mode, double value);

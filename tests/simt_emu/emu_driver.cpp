@@ -92,14 +92,20 @@ int emu_lu_solve(int N, long long n, const double* A, const double* b, double* x
 int emu_integrate(void* mv, int rt, long long n, const double* T0, const double* p0, const double* Y0, double rtol, double atol,
                   double t_end, long long mxstep, int jac_mode, int ign_mode, double ign_value, int n_out, int n_calls,
                   int nt, const double* tab_t, const double* tab_T, const double* tab_p,
-                  double* traj, double* state, double* tau, long long* stats, int* status, int warps, int linsol, double jac_clip, int pool_n) {
+                  double* traj, double* state, double* tau, long long* stats, int* status, int warps, int linsol, double jac_clip, int pool_n,
+                  int slice_steps) {
   EmuMech* m = (EmuMech*)mv;
   const int N = rt <= 1 ? m->C.K + 1 : m->C.K;
   std::vector<double> rho0(n), tcur(n);
   run_init(m, rt, n, T0, p0, Y0, state, rho0.data(), N);
   if (warps < 1) warps = 1;
-  std::vector<double> scratch((size_t)warps * warp_scratch_doubles(N, m->d.R));
+  const bool sliced = slice_steps > 0 && pool_n > 0;
+  std::vector<double> scratch((size_t)(sliced ? std::max<long long>(n, warps) : warps) * warp_scratch_doubles(N, m->d.R));
   unsigned long long counter = 0;
+  const int cap = (int)(2 * n);
+  std::vector<int> ring(cap), yielded(n);
+  std::vector<unsigned long long> ring_seq(cap), qctl(4);
+  std::vector<double> slice_save;
   BatchArgs a{};
   a.rt = rt; a.N = N; a.jac_mode = jac_mode; a.max_order = 5; a.ign_mode = ign_mode; a.fresh = 1; a.n_out = n_out; a.n = n;
   a.mxstep = mxstep; a.T0 = T0; a.p0 = p0; a.rho0 = rho0.data(); a.rtol = rtol; a.atol = atol; a.t_target = t_end; a.t_stop = t_end;
@@ -110,17 +116,25 @@ int emu_integrate(void* mv, int rt, long long n, const double* T0, const double*
   const WarpLayout L = make_layout(N, m->d.R, pool_n == 0);
   const size_t smem = ((CT_HDR_BYTES + m->d.blob_bytes + (size_t)warps * L.doubles * 8 + 15) & ~(size_t)15) + (size_t)pool_n * pool_slab_bytes(N);
   std::vector<double> save;
+  if (sliced) {
+    slice_save.assign((size_t)n * a.save_stride, 0.0);
+    a.slice_steps = slice_steps; a.ring_cap = cap; a.ring = ring.data(); a.ring_seq = ring_seq.data(); a.qctl = qctl.data();
+    a.yielded = yielded.data(); a.save = slice_save.data();
+  }
+  auto ring_init = [&]() { if (sliced) emu_launch(k_ring_init, (cap + 255) / 256, 256, 0, (int)n, cap, (const int*)nullptr, a.ring, a.ring_seq, a.qctl, a.yielded); };
   for (long long i = 0; i < n; ++i) status[i] = 0;
   if (n_calls <= 1) {
+    ring_init();
     emu_launch(k_integrate<256>, 1, 32 * warps, smem, m->d, (const unsigned char*)m->C.blob.data(), a);
   } else {
     // repeated ct_batch_integrate(t) calls with increasing targets (resumable state)
     save.assign((size_t)n * a.save_stride, 0.0);
-    a.save = save.data();
+    a.save = save.data(); a.user_save = 1;
     a.n_out = 0; a.traj = nullptr;
     for (int c = 0; c < n_calls; ++c) {
       a.t_target = (c + 1 == n_calls) ? t_end : (c + 1) * (t_end / n_calls);
       counter = 0;
+      ring_init();
       emu_launch(k_integrate<256>, 1, 32 * warps, smem, m->d, (const unsigned char*)m->C.blob.data(), a);
       a.fresh = 0;
       if (traj) for (long long i = 0; i < n; ++i) for (int k = 0; k < N; ++k) traj[((size_t)i * n_calls + c) * N + k] = state[i * N + k];

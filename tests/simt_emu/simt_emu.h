@@ -84,6 +84,7 @@ inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v)
 inline int atomicCAS(int* p, int cmp, int val) { int e = cmp; __atomic_compare_exchange_n(p, &e, val, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE); return e; }
 inline int atomicExch(int* p, int val) { return __atomic_exchange_n(p, val, __ATOMIC_ACQ_REL); }
 inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __nanosleep(unsigned) { std::this_thread::yield(); }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline double exp10(double x) { return std::pow(10.0, x); }

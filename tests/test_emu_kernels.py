@@ -36,7 +36,7 @@ def emu():
     L.emu_lu_solve.argtypes = [C.c_int, C.c_longlong, dp, dp, dp, ip, C.c_int]
     L.emu_integrate.argtypes = [C.c_void_p, C.c_int, C.c_longlong, dp, dp, dp, C.c_double, C.c_double, C.c_double, C.c_longlong,
                                 C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, lp, ip, C.c_int,
-                                C.c_int, C.c_double, C.c_int]
+                                C.c_int, C.c_double, C.c_int, C.c_int]
     L.emu_roberts.argtypes = [C.c_int, dp, C.c_double, dp, dp, lp]
     return L
 
@@ -55,7 +55,7 @@ def emech(emu, ctb):
 
 
 def _integrate(emu, h, om, rt, T0, p0, Y, rtol, atol, t_end, jac=1, linsol=0, n_out=0, n_calls=1, warps=1, mxstep=20000,
-               ign=(1, 400.0), pool_n=0):
+               ign=(1, 400.0), pool_n=0, slice_steps=0):
     n = len(T0)
     N = om.K + 1 if rt <= 1 else om.K
     T0 = np.ascontiguousarray(T0, dtype=float); p0 = np.ascontiguousarray(p0, dtype=float); Y = np.ascontiguousarray(Y, dtype=float)
@@ -63,7 +63,7 @@ def _integrate(emu, h, om, rt, T0, p0, Y, rtol, atol, t_end, jac=1, linsol=0, n_
     traj = np.zeros((n, nt, N)) if nt else None
     state = np.zeros((n, N)); tau = np.zeros(n); stats = np.zeros((n, 8), dtype=np.int64); status = np.zeros(n, dtype=np.int32)
     emu.emu_integrate(h, rt, n, P(T0), P(p0), P(Y), rtol, atol, t_end, mxstep, jac, ign[0], ign[1], n_out, n_calls, 0, None, None, None,
-                      P(traj), P(state), P(tau), stats.ctypes.data_as(lp), status.ctypes.data_as(ip), warps, linsol, 1.0, pool_n)
+                      P(traj), P(state), P(tau), stats.ctypes.data_as(lp), status.ctypes.data_as(ip), warps, linsol, 1.0, pool_n, slice_steps)
     return dict(state=state, tau=tau, stats=stats, status=status, traj=traj)
 
 
@@ -173,3 +173,30 @@ def test_work_queue_resume_and_failure_codes(emu, emech, omech):
     assert np.abs(pooled["state"][:, 0] / ref["state"][:, 0] - 1).max() < 1e-4
     inv = _integrate(emu, h, om, 1, T0, p0, Y, 1e-8, 1e-14, 2e-4, warps=2, linsol=1)
     assert np.abs(inv["state"][:, 0] / pooled["state"][:, 0] - 1).max() < 1e-6
+
+
+def test_time_slicing_is_exact(emu, emech, omech):
+    """Sliced scheduling (park the stepper every few steps, queue the reactor again, possibly resume on another warp)
+    must reproduce the uninterrupted run bit for bit: states, ignition delays, every counter, trajectories, and the
+    CV_TOO_MUCH_WORK accounting across slices."""
+    om, h = omech("gri12"), emech("gri12")
+    n = 5
+    T0 = np.array([1100.0, 1500.0, 1300.0, 1250.0, 1400.0]); p0 = np.full(n, 2 * 101325.0)
+    Y = om.X_to_Y(np.tile(om.composition({"H2": 2, "O2": 1, "N2": 3.76}), (n, 1)))
+    base = _integrate(emu, h, om, 1, T0, p0, Y, 1e-8, 1e-14, 2e-4, warps=2, linsol=1, pool_n=1)
+    for steps in (7, 40):
+        sl = _integrate(emu, h, om, 1, T0, p0, Y, 1e-8, 1e-14, 2e-4, warps=2, linsol=1, pool_n=1, slice_steps=steps)
+        assert np.array_equal(sl["status"], base["status"])
+        assert np.array_equal(sl["stats"], base["stats"])
+        assert np.array_equal(sl["state"], base["state"])
+        assert np.array_equal(sl["tau"], base["tau"], equal_nan=True)
+    tb = _integrate(emu, h, om, 1, T0, p0, Y, 1e-8, 1e-14, 2e-4, warps=2, linsol=1, pool_n=1, n_out=5)
+    ts = _integrate(emu, h, om, 1, T0, p0, Y, 1e-8, 1e-14, 2e-4, warps=2, linsol=1, pool_n=1, n_out=5, slice_steps=9)
+    assert np.array_equal(ts["traj"], tb["traj"]) and np.array_equal(ts["stats"], tb["stats"])
+    few = _integrate(emu, h, om, 1, T0, p0, Y, 1e-8, 1e-14, 2e-4, warps=2, linsol=1, pool_n=1, mxstep=20, slice_steps=7)
+    fewb = _integrate(emu, h, om, 1, T0, p0, Y, 1e-8, 1e-14, 2e-4, warps=2, linsol=1, pool_n=1, mxstep=20)
+    assert np.all(few["status"] == -1) and np.array_equal(few["stats"], fewb["stats"])
+    # repeated Integrate(t) calls (user-visible resumable state) on top of slicing
+    many = _integrate(emu, h, om, 1, T0, p0, Y, 1e-8, 1e-14, 2e-4, n_calls=3, warps=2, linsol=1, pool_n=1, slice_steps=11)
+    manyb = _integrate(emu, h, om, 1, T0, p0, Y, 1e-8, 1e-14, 2e-4, n_calls=3, warps=2, linsol=1, pool_n=1)
+    assert np.array_equal(many["state"], manyb["state"])

@@ -325,6 +325,41 @@ def test_full_size_properties(ctb, chem):
     assert st[:, 0].min() > 10 and st[:, 5].max() < 50
 
 
+def test_time_slicing_changes_nothing(ctb, chem):
+    """Scheduling options must not change a single bit: BASELINE config 2 at full size with time slicing (default),
+    with a short slice and without slicing give identical states, ignition delays and counters; the same for the
+    in-kernel trajectory grid and for repeated Integrate(t) calls."""
+    ch = chem("gri30")
+    T0 = np.repeat(np.linspace(900, 1500, 64), 64)
+    phi = np.tile(np.linspace(0.5, 2.0, 64), 64)
+    p0 = np.full(4096, 101325.0)
+    Y0 = _h2_air(ch, T0, phi)
+    res = []
+    for steps in (0, 64, 5):
+        b = ctb.ReactorBatch(ctb.Type.Const_Vol, ch, T0, p0, Y0, 1e-8, 1e-14, 1e-3, max_num_steps=50000)
+        b.SetTimeSlicing(steps)
+        assert b.Integrate(1e-3) >= 0
+        res.append((b.Solution(), b.IgnitionDelay(), b.Statistics(), b.Status(), b.LaunchCount()))
+    assert res[1][4] == res[0][4] + 1  # the ring is filled by one extra launch: slicing really ran
+    for r in res[1:]:
+        assert np.array_equal(r[0], res[0][0]) and np.array_equal(r[1], res[0][1], equal_nan=True)
+        assert np.array_equal(r[2], res[0][2]) and np.array_equal(r[3], res[0][3])
+    n = 4000  # > one wave of warps
+    sel = np.linspace(0, 4095, n).astype(int)
+    out = []
+    for steps in (0, 7):
+        b = ctb.ReactorBatch(ctb.Type.Const_Vol, ch, T0[sel], p0[sel], Y0[sel], 1e-6, 1e-12, 2e-4, max_num_steps=50000)
+        b.SetTimeSlicing(steps)
+        _, traj = b.IntegrateTrajectory(4)
+        b2 = ctb.ReactorBatch(ctb.Type.Const_Vol, ch, T0[sel], p0[sel], Y0[sel], 1e-6, 1e-12, 2e-4, max_num_steps=50000)
+        b2.SetTimeSlicing(steps)
+        for t in (0.5e-4, 1e-4, 2e-4):
+            b2.Integrate(t)
+        out.append((traj, b2.Solution(), b2.Statistics()))
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+
+
 def test_empty_and_error_paths(ctb, chem):
     ch = chem("gri30")
     b = ctb.ReactorBatch(0, ch, np.zeros(0), np.zeros(0), np.zeros((0, ch.n_species)))

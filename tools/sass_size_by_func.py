@@ -2,7 +2,7 @@
 import re, subprocess, sys, os, tempfile
 from collections import defaultdict
 kern = sys.argv[1]
-root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+root = os.environ.get("CT_ROOT", os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))  # CT_ROOT: tree whose built library was profiled
 tmp = tempfile.mkdtemp()
 subprocess.check_call("cd %s && cuobjdump -xelf all %s/chemtools_b200/libchemtools_b200.so > /dev/null" % (tmp, root), shell=True)
 cub = [f for f in os.listdir(tmp) if f.startswith("capi")][0]
