@@ -116,6 +116,8 @@ struct ct_batch {
   int64_t n = 0;
   double rtol = 1e-8, atol = 1e-14, t_stop = 1e-3;
   int64_t mxstep = 500;
+  StepOpts opts{};      // solver option surface; zero members = CVODE defaults
+  double t_start = 0.0; // integration start of a fresh batch (ct_batch_reinit)
   int max_order = 5, jac_mode = CT_JAC_ANALYTIC, ign_mode = 1, linsol = LINSOL_INVERSE;
   double ign_value = 400.0, jac_clip = 10.0;
   int gang = 1, pool_enabled = 1, pool_n = 0, pool_warps = 12, gang_groups = 1, gang_sleep_ns = 200, gang_max_polls = 0;
@@ -195,6 +197,7 @@ BatchArgs make_args(ct_batch* b) {
   a.tau = b->tau.p; a.tcur = b->tcur.p; a.stats = b->stats.p; a.status = b->status.p; a.counter = b->counter.p;
   a.scratch = b->scratch.p; a.order = b->have_order ? b->order.p : nullptr;
   a.timeline = b->timeline_on ? b->timeline.p : nullptr;
+  a.opts = b->opts; a.t_start = b->t_start;
   if (b->sliced) {
     a.slice_steps = b->slice_steps; a.ring_cap = b->ring_cap; a.ring = b->ring.p; a.ring_seq = b->ring_seq.p; a.qctl = b->qctl.p;
     a.yielded = b->yielded.p; a.save = b->save.p;
@@ -486,7 +489,7 @@ static int finish_ic(ct_batch* b) {
     CT_CUDA(cudaGetLastError());
     b->aux_launches += 1;
   }
-  b->have_ic = true; b->fresh = true;
+  b->have_ic = true; b->fresh = true; b->t_start = 0.0;
   return 0;
 }
 int ct_batch_set_ic(ct_batch* b, const double* T, const double* p, const double* Y) {
@@ -521,6 +524,65 @@ int ct_batch_set_max_order(ct_batch* b, int q) {
   if (!b) return fail(CT_ERR_INVALID, "null batch");
   if (q < 1 || q > 5) return fail(CT_ILL_INPUT, "BDF order must be in 1..5");
   b->max_order = q;
+  return 0;
+}
+// IStrategy::SetInitStepSize / SetMinStepSize / SetMaxStepSize (interface.cpp:61-97): negative values are invalid,
+// 0 selects CVODE's default (estimated first step, hmin = 0, hmax = infinity)
+int ct_batch_set_init_step(ct_batch* b, double h) {
+  if (!b) return fail(CT_ERR_INVALID, "null batch");
+  if (!(h >= 0.0)) return fail(CT_ILL_INPUT, "SetInitStepSize: initial step size must be non-negative");
+  b->opts.h_init = h;
+  return 0;
+}
+int ct_batch_set_min_step(ct_batch* b, double h) {
+  if (!b) return fail(CT_ERR_INVALID, "null batch");
+  if (!(h >= 0.0)) return fail(CT_ILL_INPUT, "SetMinStepSize: minimum step size must be non-negative");
+  if (h > 0.0 && b->opts.h_max_inv > 0.0 && h * b->opts.h_max_inv > 1.0) return fail(CT_ILL_INPUT, "SetMinStepSize: minimum step exceeds maximum step");
+  b->opts.h_min = h;
+  return 0;
+}
+int ct_batch_set_max_step(ct_batch* b, double h) {
+  if (!b) return fail(CT_ERR_INVALID, "null batch");
+  if (!(h >= 0.0)) return fail(CT_ILL_INPUT, "SetMaxStepSize: maximum step size must be non-negative");
+  if (h > 0.0 && h < b->opts.h_min) return fail(CT_ILL_INPUT, "SetMaxStepSize: maximum step below minimum step");
+  b->opts.h_max_inv = h > 0.0 ? 1.0 / h : 0.0;
+  return 0;
+}
+// IStrategy::SetMaxErrorTestFailures / SetMaxNonlinearIterations / SetMaxConvergenceFailures /
+// SetNonlinConvergenceCoefficient (interface.cpp:166-219): must be positive; defaults 7 / 3 / 10 / 0.1 (types.hpp:97-111)
+int ct_batch_set_max_err_test_fails(ct_batch* b, int n) {
+  if (!b) return fail(CT_ERR_INVALID, "null batch");
+  if (n <= 0) return fail(CT_ILL_INPUT, "SetMaxErrorTestFailures: must be positive");
+  b->opts.max_nef = n;
+  return 0;
+}
+int ct_batch_set_max_nonlin_iters(ct_batch* b, int n) {
+  if (!b) return fail(CT_ERR_INVALID, "null batch");
+  if (n <= 0) return fail(CT_ILL_INPUT, "SetMaxNonlinearIterations: must be positive");
+  b->opts.max_cor = n;
+  return 0;
+}
+int ct_batch_set_max_conv_fails(ct_batch* b, int n) {
+  if (!b) return fail(CT_ERR_INVALID, "null batch");
+  if (n <= 0) return fail(CT_ILL_INPUT, "SetMaxConvergenceFailures: must be positive");
+  b->opts.max_ncf = n;
+  return 0;
+}
+int ct_batch_set_nonlin_conv_coef(ct_batch* b, double c) {
+  if (!b) return fail(CT_ERR_INVALID, "null batch");
+  if (!(c > 0.0)) return fail(CT_ILL_INPUT, "SetNonlinConvergenceCoefficient: must be positive");
+  b->opts.nls_coef = c;
+  return 0;
+}
+// IStrategy::ReInitialise(time_init, state) (interface.cpp:429-446) -> CVodeReInit: new start time and state, all
+// options, tolerances and the reactors' frozen parameters (pressure / density of the original initial conditions) kept
+int ct_batch_reinit(ct_batch* b, double t0, const double* state) {
+  if (!b || !state) return fail(CT_ERR_INVALID, "null argument");
+  if (!b->have_ic) return fail(CT_ILL_INPUT, "ReInitialise before the initial conditions were set");
+  if (!(t0 < b->t_stop)) return fail(CT_ILL_INPUT, "ReInitialise: start time must precede the stop time");
+  if (b->n > 0) CT_CUDA(cudaMemcpyAsync(b->state.p, state, (size_t)b->n * b->N * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+  CT_CUDA(cudaStreamSynchronize(b->stream));
+  b->t_start = t0; b->fresh = true;
   return 0;
 }
 int ct_batch_set_jacobian(ct_batch* b, int mode) {
@@ -615,6 +677,7 @@ int ct_batch_integrate(ct_batch* b, double t_target) {
   if (int r = precheck_integrate(b)) return r;
   if (b->n == 0) return CT_SUCCESS;
   if (!(t_target > 0.0)) return fail(CT_ILL_INPUT, "t_target must be positive");
+  if (b->fresh && !(t_target > b->t_start)) return fail(CT_ILL_INPUT, "t_target must follow the start time");
   BatchArgs a = make_args(b);
   a.t_target = t_target;
   const bool resumable = t_target < b->t_stop || !b->fresh;

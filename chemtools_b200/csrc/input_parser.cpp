@@ -198,9 +198,9 @@ double convert_unit(double v, const std::string& unit, int dim, const char* targ
   throw InputError(InputError::InvalidArgument, unit + " is not a valid unit.");
 }
 
-const YamlNode& need(const YamlNode& map, const char* key, const std::string& ctx) {
+const YamlNode& need(const YamlNode& map, const char* key, const char* ctx) {
   const YamlNode* n = map.find(key);
-  if (!n || n->kind == YamlNode::Null) throw InputError(InputError::InvalidNode, "missing mandatory key '" + std::string(key) + "' in " + ctx);
+  if (!n || n->kind == YamlNode::Null) throw InputError(InputError::InvalidNode, "missing mandatory key '" + std::string(key) + "' in " + std::string(ctx));
   return *n;
 }
 double as_double(const YamlNode& n, const std::string& ctx) {

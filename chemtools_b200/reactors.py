@@ -175,6 +175,34 @@ class ReactorBatch:
     def SetMaxOrder(self, q):
         check(lib().ct_batch_set_max_order(self._h, int(q)))
 
+    def SetInitStepSize(self, h):
+        check(lib().ct_batch_set_init_step(self._h, float(h)))
+
+    def SetMinStepSize(self, h):
+        check(lib().ct_batch_set_min_step(self._h, float(h)))
+
+    def SetMaxStepSize(self, h):
+        check(lib().ct_batch_set_max_step(self._h, float(h)))
+
+    def SetMaxErrorTestFailures(self, n):
+        check(lib().ct_batch_set_max_err_test_fails(self._h, int(n)))
+
+    def SetMaxNonlinearIterations(self, n):
+        check(lib().ct_batch_set_max_nonlin_iters(self._h, int(n)))
+
+    def SetMaxConvergenceFailures(self, n):
+        check(lib().ct_batch_set_max_conv_fails(self._h, int(n)))
+
+    def SetNonlinConvergenceCoefficient(self, c):
+        check(lib().ct_batch_set_nonlin_conv_coef(self._h, float(c)))
+
+    def ReInitialise(self, time_init, state):
+        """IStrategy::ReInitialise (interface.cpp:429-446): restart from state[n, N] at time_init."""
+        st = _f64(np.atleast_2d(state))
+        if st.shape != (self.n, self.n_state):
+            raise ValueError("state must have shape (n, n_state)")
+        check(lib().ct_batch_reinit(self._h, float(time_init), _p(st)))
+
     def SetJacobian(self, mode):
         check(lib().ct_batch_set_jacobian(self._h, {"dq": 0, "analytic": 1}.get(mode, mode)))
 

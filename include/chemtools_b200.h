@@ -125,6 +125,20 @@ int ct_batch_set_stop_time(ct_batch*, double t_end);
 int ct_batch_set_max_steps(ct_batch*, int64_t mxstep);
 /* Solver::SetMaxOrder (interface.hpp:83), 1..5 */
 int ct_batch_set_max_order(ct_batch*, int q);
+/* Solver option surface, same names, validation and defaults as IStrategy::Set* (interface.hpp:77-89,
+ * src/sundials/cvode/interface.cpp:61-219, defaults include/sundials/cvode/types.hpp:68-112).  Step sizes: negative ->
+ * CT_ILL_INPUT, 0 = CVODE default (estimated h0, hmin 0, hmax inf).  Counts / coefficient: must be positive; defaults
+ * 7 error-test failures, 3 Newton iterations, 10 convergence failures, coefficient 0.1 */
+int ct_batch_set_init_step(ct_batch*, double h);
+int ct_batch_set_min_step(ct_batch*, double h);
+int ct_batch_set_max_step(ct_batch*, double h);
+int ct_batch_set_max_err_test_fails(ct_batch*, int n);
+int ct_batch_set_max_nonlin_iters(ct_batch*, int n);
+int ct_batch_set_max_conv_fails(ct_batch*, int n);
+int ct_batch_set_nonlin_conv_coef(ct_batch*, double coef);
+/* IStrategy::ReInitialise(time_init, state) (interface.cpp:429-446): restart every reactor from state[n x N] at t0,
+ * keeping options, tolerances and the frozen reactor parameters of the original initial conditions */
+int ct_batch_reinit(ct_batch*, double t0, const double* state);
 int ct_batch_set_jacobian(ct_batch*, int mode);
 /* Newton linear algebra: CT_LINSOL_LU = LU + triangular solves (what SUNLinSol_Dense does, interface.cpp:714-721);
  * CT_LINSOL_INVERSE (default) = Gauss-Jordan inverse of the error-weight-equilibrated I - gamma*J once per setup, each

@@ -21,6 +21,7 @@ typedef struct {
   const omech* m; int type; long n; const double *T0, *p0, *Y0; int nt; const double *tab_t, *tab_T, *tab_p;
   double rtol, atol, t_end; long max_steps; int ign_mode; double ign_value; int n_out;
   double *out_traj, *out_state, *out_tau; long* out_stats; int* out_status;
+  const double* opts;
   atomic_long next;
 } batch_job;
 
@@ -38,6 +39,12 @@ static void run_one(batch_job* J, long i) {
   cvo_set_tolerances(c, J->rtol, J->atol, NULL);
   cvo_set_stop_time(c, J->t_end);
   cvo_set_max_steps(c, J->max_steps);
+  if (J->opts) {
+    const double* o = J->opts;
+    cvo_set_step_options(c, o[0], o[1], o[2]);
+    cvo_set_solver_options(c, (int)o[4], (int)o[5], (int)o[6], o[3]);
+    if (o[7] > 0) cvo_set_max_order(c, (int)o[7]);
+  }
   if (J->type <= OR_CONST_VOL) cvo_watch(c, 0, J->ign_mode == 0 ? J->ign_value : J->T0[i] + J->ign_value);
   int status = 0;
   double tret = 0.0;
@@ -83,8 +90,18 @@ int or_integrate_batch(const omech* m, int type, long n, const double* T0, const
                        const double* tab_p, double rtol, double atol, double t_end, long max_steps,
                        int ign_mode, double ign_value, int nthreads, int n_out, double* out_traj,
                        double* out_state, double* out_tau, long* out_stats, int* out_status) {
+  return or_integrate_batch_opts(m, type, n, T0, p0, Y0, nt, tab_t, tab_T, tab_p, rtol, atol, t_end, max_steps, ign_mode,
+                                 ign_value, nthreads, n_out, out_traj, out_state, out_tau, out_stats, out_status, NULL);
+}
+
+int or_integrate_batch_opts(const omech* m, int type, long n, const double* T0, const double* p0,
+                            const double* Y0, int nt, const double* tab_t, const double* tab_T,
+                            const double* tab_p, double rtol, double atol, double t_end, long max_steps,
+                            int ign_mode, double ign_value, int nthreads, int n_out, double* out_traj,
+                            double* out_state, double* out_tau, long* out_stats, int* out_status,
+                            const double* opts) {
   batch_job J = {m, type, n, T0, p0, Y0, nt, tab_t, tab_T, tab_p, rtol, atol, t_end, max_steps,
-                 ign_mode, ign_value, n_out, out_traj, out_state, out_tau, out_stats, out_status, 0};
+                 ign_mode, ign_value, n_out, out_traj, out_state, out_tau, out_stats, out_status, opts, 0};
   if (nthreads < 1) nthreads = 1;
   if (nthreads > n) nthreads = (int)(n > 0 ? n : 1);
   if (nthreads == 1) { worker(&J); return 0; }

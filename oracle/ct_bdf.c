@@ -78,7 +78,7 @@ struct cvo {
   double rl1, gamma, gammap, gamrat, crate, delp, acnrm;
   int acnrmcur;
   double etamax, etaq, etaqm1, etaqp1, saved_tq5;
-  double hmin, hmax_inv, nlscoef;
+  double hmin, hmax_inv, nlscoef, hin; /* hin: user initial step (CVodeSetInitStep), 0 = estimate */
   int maxnef, maxncf, maxcor;
   long mxstep, nst, nfe, nsetups, netf, nni, ncfn, nje, nfeDQ, nstlp, nstlj;
   int tstopset; double tstop;
@@ -138,6 +138,19 @@ void cvo_set_tolerances(cvo* c, double rtol, double atol_s, const double* atol_v
 void cvo_set_stop_time(cvo* c, double tstop) { c->tstop = tstop; c->tstopset = 1; }
 void cvo_set_max_steps(cvo* c, long mx) { c->mxstep = mx > 0 ? mx : 500; }
 void cvo_set_max_order(cvo* c, int q) { if (q >= 1 && q <= QMAX) c->qmax = q; }
+/* CVodeSetInitStep / SetMinStep / SetMaxStep (IStrategy::SetInitStepSize..., interface.cpp:61-97 of the reference):
+ * 0 keeps CVODE's default (estimated h0, hmin = 0, hmax = inf) */
+void cvo_set_step_options(cvo* c, double h_init, double h_min, double h_max) {
+  c->hin = h_init; c->hmin = h_min > 0.0 ? h_min : 0.0; c->hmax_inv = h_max > 0.0 ? 1.0 / h_max : 0.0;
+}
+/* CVodeSetMaxErrTestFails / SetMaxNonlinIters / SetMaxConvFails / SetNonlinConvCoef (interface.cpp:166-219);
+ * non-positive values keep the defaults 7 / 3 / 10 / 0.1 */
+void cvo_set_solver_options(cvo* c, int maxnef, int maxcor, int maxncf, double nlscoef) {
+  if (maxnef > 0) c->maxnef = maxnef;
+  if (maxcor > 0) c->maxcor = maxcor;
+  if (maxncf > 0) c->maxncf = maxncf;
+  if (nlscoef > 0.0) c->nlscoef = nlscoef;
+}
 void cvo_watch(cvo* c, int comp, double thr) { c->watch_comp = comp; c->watch_thr = thr; c->watch_done = 0; c->watch_time = NAN; }
 double cvo_watch_time(const cvo* c) { return c->watch_time; }
 void cvo_stats(const cvo* c, long* io, double* ro) {
@@ -579,8 +592,9 @@ int cvo_integrate(cvo* c, double tout, double* yout, double* tret) {
     if (c->f(c->tn, c->zn[0], c->zn[1], c->user)) return -8;
     c->nfe++;
     if (c->tstopset && (c->tstop - c->tn) * (tout - c->tn) <= 0.0) return CVO_ILL_INPUT;
-    c->h = 0.0;
-    {
+    c->h = c->hin;
+    if (c->h != 0.0 && (tout - c->tn) * c->h < 0.0) return CVO_ILL_INPUT;
+    if (c->h == 0.0) {
       double tout_hin = tout;
       if (c->tstopset && (tout - c->tn) * (tout - c->tstop) > 0.0) tout_hin = c->tstop;
       int r = cv_hin(c, tout_hin);

@@ -73,6 +73,8 @@ void cvo_set_tolerances(cvo*, double rtol, double atol_scalar, const double* ato
 void cvo_set_stop_time(cvo*, double tstop);
 void cvo_set_max_steps(cvo*, long mxstep);
 void cvo_set_max_order(cvo*, int q);
+void cvo_set_step_options(cvo*, double h_init, double h_min, double h_max); /* 0 = CVODE default */
+void cvo_set_solver_options(cvo*, int maxnef, int maxcor, int maxncf, double nlscoef); /* <= 0 = default */
 /* CVode(..., CV_NORMAL). returns 0 CV_SUCCESS, 1 CV_TSTOP_RETURN, <0 failure */
 int cvo_integrate(cvo*, double tout, double* yout, double* tret);
 /* nst nfe nsetups netf nni ncfn nje nfeDQ qlast qcur ; hlast hcur h0u tcur */
@@ -94,6 +96,14 @@ int or_integrate_batch(const omech*, int type, long n, const double* T0, const d
                        const double* tab_p, double rtol, double atol, double t_end, long max_steps,
                        int ign_mode, double ign_value, int nthreads, int n_out, double* out_traj,
                        double* out_state, double* out_tau, long* out_stats, int* out_status);
+/* same with the solver option surface of the reference (types.hpp:68-112): opts[8] = h_init, h_min, h_max, nls_coef,
+ * max_err_test_fails, max_nonlin_iters, max_conv_fails, max_order (0 = default); NULL = all defaults */
+int or_integrate_batch_opts(const omech*, int type, long n, const double* T0, const double* p0,
+                            const double* Y0, int nt, const double* tab_t, const double* tab_T,
+                            const double* tab_p, double rtol, double atol, double t_end, long max_steps,
+                            int ign_mode, double ign_value, int nthreads, int n_out, double* out_traj,
+                            double* out_state, double* out_tau, long* out_stats, int* out_status,
+                            const double* opts);
 int or_rhs_batch(const omech*, int type, long n, const double* T0, const double* p0, const double* Y0,
                  const double* states, double* ydot, double* wdot, double* qf, double* qr);
 

@@ -80,6 +80,7 @@ def lib():
         L.or_integrate_batch.argtypes = [C.c_void_p, C.c_int, C.c_long, dp, dp, dp, C.c_int, dp, dp, dp,
                                          C.c_double, C.c_double, C.c_double, C.c_long, C.c_int, C.c_double,
                                          C.c_int, C.c_int, dp, dp, dp, lp, ip]
+        L.or_integrate_batch_opts.argtypes = L.or_integrate_batch.argtypes + [dp]
         L.or_rhs_batch.argtypes = [C.c_void_p, C.c_int, C.c_long, dp, dp, dp, dp, dp, dp, dp, dp]
         _LIB = L
     return _LIB
@@ -247,7 +248,7 @@ class Mechanism:
         return ydot, wdot, qf, qr
 
     def integrate_batch(self, rtype, T0, p0, Y0, t_end, rtol=1e-8, atol=1e-14, max_steps=20000, ign_mode=1,
-                        ign_value=400.0, nthreads=1, n_out=0, table=None):
+                        ign_value=400.0, nthreads=1, n_out=0, table=None, options=None):
         """One Apps::Reactor + CVODE(BDF, dense, DQ Jacobian) per case, 0 -> t_end."""
         rtype = REACTOR_TYPES.get(rtype, rtype)
         T0, p0, Y0 = _f64(np.atleast_1d(T0)), _f64(np.atleast_1d(p0)), _f64(np.atleast_2d(Y0))
@@ -259,9 +260,14 @@ class Mechanism:
         if table is not None:
             tt, tT, tp = (_f64(a) for a in table)
             nt = tt.shape[0]
-        lib().or_integrate_batch(self._h, rtype, n, _dp(T0), _dp(p0), _dp(Y0), nt, _dp(tt), _dp(tT), _dp(tp), rtol, atol,
-                                 t_end, max_steps, ign_mode, ign_value, nthreads, n_out, _dp(traj), _dp(state), _dp(tau),
-                                 stats.ctypes.data_as(C.POINTER(C.c_long)), _ip(status))
+        opts = None
+        if options:
+            # solver option surface of the reference (types.hpp:68-112); 0 = CVODE default
+            opts = _f64([options.get(k, 0.0) for k in ("init_step", "min_step", "max_step", "nonlin_conv_coef",
+                                                        "max_err_test_fails", "max_nonlin_iters", "max_conv_fails", "max_order")])
+        lib().or_integrate_batch_opts(self._h, rtype, n, _dp(T0), _dp(p0), _dp(Y0), nt, _dp(tt), _dp(tT), _dp(tp), rtol, atol,
+                                      t_end, max_steps, ign_mode, ign_value, nthreads, n_out, _dp(traj), _dp(state), _dp(tau),
+                                      stats.ctypes.data_as(C.POINTER(C.c_long)), _ip(status), _dp(opts))
         return dict(state=state, tau=tau, stats=stats, status=status, traj=traj)
 
 

@@ -93,7 +93,7 @@ int emu_integrate(void* mv, int rt, long long n, const double* T0, const double*
                   double t_end, long long mxstep, int jac_mode, int ign_mode, double ign_value, int n_out, int n_calls,
                   int nt, const double* tab_t, const double* tab_T, const double* tab_p,
                   double* traj, double* state, double* tau, long long* stats, int* status, int warps, int linsol, double jac_clip, int pool_n,
-                  int slice_steps) {
+                  int slice_steps, const double* opts /* 8 or null: h_init h_min h_max nls_coef max_nef max_cor max_ncf max_order */) {
   EmuMech* m = (EmuMech*)mv;
   const int N = rt <= 1 ? m->C.K + 1 : m->C.K;
   std::vector<double> rho0(n), tcur(n);
@@ -113,6 +113,11 @@ int emu_integrate(void* mv, int rt, long long n, const double* T0, const double*
   a.ign_value = ign_value; a.state = state; a.traj = traj; a.tau = tau; a.tcur = tcur.data(); a.stats = stats; a.status = status;
   a.counter = &counter; a.scratch = scratch.data(); a.linsol = linsol; a.jac_clip = jac_clip; a.gang = 1; a.pool_n = pool_n;
   a.save_stride = CT_LMAX * CT_NP + CT_SAVE_SCALARS;
+  if (opts) {
+    a.opts.h_init = opts[0]; a.opts.h_min = opts[1]; a.opts.h_max_inv = opts[2] > 0 ? 1.0 / opts[2] : 0.0; a.opts.nls_coef = opts[3];
+    a.opts.max_nef = (int)opts[4]; a.opts.max_cor = (int)opts[5]; a.opts.max_ncf = (int)opts[6];
+    if (opts[7] > 0) a.max_order = (int)opts[7];
+  }
   const WarpLayout L = make_layout(N, m->d.R, pool_n == 0);
   const size_t smem = ((CT_HDR_BYTES + m->d.blob_bytes + (size_t)warps * L.doubles * 8 + 15) & ~(size_t)15) + (size_t)pool_n * pool_slab_bytes(N);
   std::vector<double> save;

@@ -36,7 +36,7 @@ def emu():
     L.emu_lu_solve.argtypes = [C.c_int, C.c_longlong, dp, dp, dp, ip, C.c_int]
     L.emu_integrate.argtypes = [C.c_void_p, C.c_int, C.c_longlong, dp, dp, dp, C.c_double, C.c_double, C.c_double, C.c_longlong,
                                 C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, lp, ip, C.c_int,
-                                C.c_int, C.c_double, C.c_int, C.c_int]
+                                C.c_int, C.c_double, C.c_int, C.c_int, dp]
     L.emu_roberts.argtypes = [C.c_int, dp, C.c_double, dp, dp, lp]
     return L
 
@@ -54,16 +54,23 @@ def emech(emu, ctb):
     return get
 
 
+OPTION_KEYS = ("init_step", "min_step", "max_step", "nonlin_conv_coef", "max_err_test_fails", "max_nonlin_iters",
+               "max_conv_fails", "max_order")
+
+
 def _integrate(emu, h, om, rt, T0, p0, Y, rtol, atol, t_end, jac=1, linsol=0, n_out=0, n_calls=1, warps=1, mxstep=20000,
-               ign=(1, 400.0), pool_n=0, slice_steps=0):
+               ign=(1, 400.0), pool_n=0, slice_steps=0, options=None):
     n = len(T0)
     N = om.K + 1 if rt <= 1 else om.K
     T0 = np.ascontiguousarray(T0, dtype=float); p0 = np.ascontiguousarray(p0, dtype=float); Y = np.ascontiguousarray(Y, dtype=float)
     nt = max(n_out, n_calls if n_calls > 1 else 0)
     traj = np.zeros((n, nt, N)) if nt else None
     state = np.zeros((n, N)); tau = np.zeros(n); stats = np.zeros((n, 8), dtype=np.int64); status = np.zeros(n, dtype=np.int32)
+    opts = None
+    if options:
+        opts = np.array([options.get(k, 0.0) for k in OPTION_KEYS], dtype=float)
     emu.emu_integrate(h, rt, n, P(T0), P(p0), P(Y), rtol, atol, t_end, mxstep, jac, ign[0], ign[1], n_out, n_calls, 0, None, None, None,
-                      P(traj), P(state), P(tau), stats.ctypes.data_as(lp), status.ctypes.data_as(ip), warps, linsol, 1.0, pool_n, slice_steps)
+                      P(traj), P(state), P(tau), stats.ctypes.data_as(lp), status.ctypes.data_as(ip), warps, linsol, 1.0, pool_n, slice_steps, P(opts))
     return dict(state=state, tau=tau, stats=stats, status=status, traj=traj)
 
 
@@ -200,3 +207,27 @@ def test_time_slicing_is_exact(emu, emech, omech):
     many = _integrate(emu, h, om, 1, T0, p0, Y, 1e-8, 1e-14, 2e-4, n_calls=3, warps=2, linsol=1, pool_n=1, slice_steps=11)
     manyb = _integrate(emu, h, om, 1, T0, p0, Y, 1e-8, 1e-14, 2e-4, n_calls=3, warps=2, linsol=1, pool_n=1)
     assert np.array_equal(many["state"], manyb["state"])
+
+
+def test_solver_option_surface_vs_oracle(emu, emech, omech):
+    """IStrategy::Set* options (interface.cpp:61-219 of the reference): initial / minimum / maximum step, Newton
+    iterations and coefficient, failure limits, maximum order — device stepper source against the oracle's CVODE
+    restatement with the same options."""
+    om, h = omech("gri12"), emech("gri12")
+    T0 = np.array([1250.0, 1500.0]); p0 = np.full(2, 2 * 101325.0)
+    Y = om.X_to_Y(np.tile(om.composition({"H2": 2, "O2": 1, "N2": 3.76}), (2, 1)))
+    opts = dict(init_step=1e-10, max_step=4e-6, nonlin_conv_coef=0.05, max_nonlin_iters=4, max_err_test_fails=5,
+                max_conv_fails=8, max_order=3)
+    ref = om.integrate_batch(1, T0, p0, Y, 2e-4, rtol=1e-8, atol=1e-14, max_steps=20000, options=opts)
+    dflt = om.integrate_batch(1, T0, p0, Y, 2e-4, rtol=1e-8, atol=1e-14, max_steps=20000)
+    got = _integrate(emu, h, om, 1, T0, p0, Y, 1e-8, 1e-14, 2e-4, jac=0, options=opts)  # DQ Jacobian + LU like the oracle
+    assert np.all(got["status"] == ref["status"]) and np.all(ref["status"] >= 0)
+    assert np.abs(got["state"][:, 0] / ref["state"][:, 0] - 1).max() < 1e-6
+    assert np.abs(got["tau"] / ref["tau"] - 1).max() < 1e-5
+    assert np.abs(got["stats"][:, 0] / ref["stats"][:, 0] - 1).max() < 0.05
+    assert np.all(ref["stats"][:, 0] > 1.2 * dflt["stats"][:, 0])  # the options really changed the integration
+    # a minimum step the ignition front cannot live with: same failure class as CVODE's
+    bad = dict(min_step=2e-6)
+    refb = om.integrate_batch(1, T0, p0, Y, 2e-4, rtol=1e-8, atol=1e-14, max_steps=20000, options=bad)
+    gotb = _integrate(emu, h, om, 1, T0, p0, Y, 1e-8, 1e-14, 2e-4, jac=0, options=bad)
+    assert np.all(refb["status"] < 0) and np.array_equal(gotb["status"], refb["status"])

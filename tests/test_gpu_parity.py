@@ -360,6 +360,52 @@ def test_time_slicing_changes_nothing(ctb, chem):
     assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
 
 
+def test_solver_options_and_reinitialise(ctb, chem, omech):
+    """Option surface of the reference's Solver (interface.hpp:77-89) against the oracle with the same options, the
+    setters' validation (interface.cpp:61-219), and ReInitialise (interface.cpp:429-446)."""
+    ch, om = chem("gri30"), omech("gri30")
+    T0 = np.linspace(1050.0, 1450.0, 8); p0 = np.full(8, 101325.0)
+    Y0 = _h2_air(ch, T0, np.full(8, 1.0))
+    opts = dict(init_step=1e-10, max_step=4e-6, nonlin_conv_coef=0.05, max_nonlin_iters=4, max_err_test_fails=5,
+                max_conv_fails=8, max_order=3)
+    ref = om.integrate_batch(1, T0, p0, Y0, 1e-3, rtol=1e-8, atol=1e-14, max_steps=50000, options=opts, nthreads=8)
+    dflt = om.integrate_batch(1, T0, p0, Y0, 1e-3, rtol=1e-8, atol=1e-14, max_steps=50000, nthreads=8)
+    b = ctb.ReactorBatch(1, ch, T0, p0, Y0, 1e-8, 1e-14, 1e-3, max_num_steps=50000)
+    b.SetInitStepSize(1e-10); b.SetMaxStepSize(4e-6); b.SetNonlinConvergenceCoefficient(0.05)
+    b.SetMaxNonlinearIterations(4); b.SetMaxErrorTestFailures(5); b.SetMaxConvergenceFailures(8); b.SetMaxOrder(3)
+    assert b.Integrate(1e-3) >= 0
+    st = b.Statistics()
+    assert np.abs(b.Temperature() / ref["state"][:, 0] - 1).max() < 1e-4
+    ok = np.isfinite(ref["tau"])
+    assert ok.sum() >= 4 and np.abs(b.IgnitionDelay()[ok] / ref["tau"][ok] - 1).max() < 5e-4
+    assert np.abs(st[:, 0] / ref["stats"][:, 0] - 1).max() < 0.15
+    assert np.all(st[:, 0] > 1.2 * dflt["stats"][:, 0])
+    # validation like the reference's setters
+    for call, bad in ((b.SetInitStepSize, -1.0), (b.SetMinStepSize, -1e-9), (b.SetMaxStepSize, -1.0), (b.SetMaxErrorTestFailures, 0),
+                      (b.SetMaxNonlinearIterations, 0), (b.SetMaxConvergenceFailures, -2), (b.SetNonlinConvergenceCoefficient, 0.0)):
+        with pytest.raises(ctb.reactors.CtError):
+            call(bad)
+    # minimum step too large for the ignition front: CVODE's failure class per reactor, same as the oracle
+    refm = om.integrate_batch(1, T0, p0, Y0, 1e-3, rtol=1e-8, atol=1e-14, max_steps=50000, options=dict(min_step=2e-6), nthreads=8)
+    bm = ctb.ReactorBatch(1, ch, T0, p0, Y0, 1e-8, 1e-14, 1e-3, max_num_steps=50000)
+    bm.SetMinStepSize(2e-6)
+    code = bm.Integrate(1e-3)
+    assert np.array_equal(np.sign(bm.Status()), np.sign(refm["status"])) and code == bm.Status().min()
+    # ReInitialise: stop at 0.3 ms, restart from the returned state at that time, end at the same answer
+    c = ctb.ReactorBatch(1, ch, T0, p0, Y0, 1e-9, 1e-15, 1e-3, max_num_steps=50000)
+    assert c.Integrate(1e-3) >= 0
+    full = c.Solution()
+    r = ctb.ReactorBatch(1, ch, T0, p0, Y0, 1e-9, 1e-15, 1e-3, max_num_steps=50000)
+    assert r.Integrate(3e-4) == 0
+    mid = r.Solution()
+    r.ReInitialise(3e-4, mid)
+    assert r.Integrate(1e-3) in (0, 1) and np.allclose(r.Time(), 1e-3)  # CV_SUCCESS or CV_TSTOP_RETURN: tout == tstop
+    assert np.abs(r.Solution()[:, 0] / full[:, 0] - 1).max() < 1e-4
+    assert r.Statistics()[:, 0].max() < c.Statistics()[:, 0].max()  # counters restart with the integrator
+    with pytest.raises(ctb.reactors.CtError):
+        r.ReInitialise(2e-3, mid)  # start time beyond the stop time
+
+
 def test_empty_and_error_paths(ctb, chem):
     ch = chem("gri30")
     b = ctb.ReactorBatch(0, ch, np.zeros(0), np.zeros(0), np.zeros((0, ch.n_species)))
