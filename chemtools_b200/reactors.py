@@ -245,6 +245,27 @@ class ReactorBatch:
             raise ValueError("table shapes must be [n, nt]")
         check(lib().ct_batch_set_tp_table(self._h, t.shape[0], _p(t), _p(T), _p(p)))
 
+    def SetTableFromFunction(self, function, n_points=101, module_path=None):
+        """Prescribed T(t), p(t) from a FunctionP1R2-style Python callable (include/embedded_python/functions.hpp:10-41
+        of the reference: one parameter in, two values out).  `function` is a callable f(t) -> (T, p), or a function
+        name to load from the module file `module_path` like FunctionP1R2::Load(module_path, function_name).  The
+        callable is sampled ONCE on the host at n_points equidistant times in [0, t_end] into the device table (linear
+        interpolation in the kernel); T and p may be scalars (all reactors) or arrays of length n."""
+        if module_path is not None:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("ct_user_profile", module_path)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            function = getattr(mod, function)
+        t = np.linspace(0.0, self.t_end, int(n_points))
+        T = np.zeros((self.n, t.size)); p = np.zeros((self.n, t.size))
+        for k, tk in enumerate(t):
+            val = function(float(tk))
+            if len(val) != 2:
+                raise ValueError("the profile function must return two values (T, p)")
+            T[:, k] = val[0]; p[:, k] = val[1]
+        self.SetTable(t, T, p)
+
     def SetOrder(self, order):
         o = np.ascontiguousarray(order, dtype=np.int32)
         if o.shape != (self.n,):

@@ -275,7 +275,7 @@ def test_ensemble_parity(ctb, chem, omech, cfg, tols):
     assert np.all(st[:, 0] > 0) and np.all(st[:, 6] <= st[:, 2])
 
 
-def test_table_reactor_integration(ctb, chem, omech):
+def test_table_reactor_integration(ctb, chem, omech, tmp_path):
     """BASELINE config 4 (sample): prescribed T(t), p(t) tables."""
     ch, om = chem("gri30"), omech("gri30")
     rng = np.random.default_rng(30)
@@ -295,6 +295,18 @@ def test_table_reactor_integration(ctb, chem, omech):
     assert (np.abs(Y - Yo).max(1) / np.abs(Yo).max(1)).max() < TRAJ_TOL
     major = Yo > 1e-6
     assert np.abs(Y[major] / Yo[major] - 1).max() < 1e-3
+    # the same profiles from a FunctionP1R2-style Python callable, sampled on the host into the table
+    b2 = ctb.ReactorBatch(ctb.Type.Table_Temp_Pres, ch, Ta, pa, Y0, 1e-8, 1e-14, t_end, max_num_steps=2000000)
+    b2.SetTableFromFunction(lambda t: (Ta + (Tb - Ta) * t / t_end, pa * (1 + 0.5 * t / t_end)), n_points=nt)
+    assert b2.Integrate(t_end) >= 0 and np.array_equal(b2.MassFractions(), Y)
+    mod = tmp_path / "profile.py"
+    mod.write_text("def ramp(t):\n    T = 1000.0 + 8.0e5 * t\n    p = 101325.0 * (1.0 + 500.0 * t)\n    return (T, p)\n")
+    b3 = ctb.ReactorBatch(ctb.Type.Table_Temp_Pres, ch, Ta, pa, Y0, 1e-8, 1e-14, t_end, max_num_steps=2000000)
+    b3.SetTableFromFunction("ramp", n_points=11, module_path=str(mod))
+    b4 = ctb.ReactorBatch(ctb.Type.Table_Temp_Pres, ch, Ta, pa, Y0, 1e-8, 1e-14, t_end, max_num_steps=2000000)
+    t11 = np.linspace(0, t_end, 11)
+    b4.SetTable(t11, np.tile(1000.0 + 8.0e5 * t11, (n, 1)), np.tile(101325.0 * (1.0 + 500.0 * t11), (n, 1)))
+    assert b3.Integrate(t_end) >= 0 and b4.Integrate(t_end) >= 0 and np.array_equal(b3.MassFractions(), b4.MassFractions())
 
 
 def test_full_size_properties(ctb, chem):

@@ -11,19 +11,27 @@ root = os.environ.get("CT_ROOT", os.path.join(os.path.dirname(os.path.abspath(__
 tmp = tempfile.mkdtemp()
 subprocess.check_call("cd %s && cuobjdump -xelf all %s/chemtools_b200/libchemtools_b200.so > /dev/null" % (tmp, root), shell=True)
 cub = [f for f in os.listdir(tmp) if f.startswith("capi")][0]
-sass = subprocess.check_output(["nvdisasm", "--print-line-info", os.path.join(tmp, cub)], text=True, stderr=subprocess.DEVNULL).split("\n")
+sass = subprocess.check_output(["nvdisasm", "--print-line-info-inline" if os.environ.get("CT_INLINE") else "--print-line-info", os.path.join(tmp, cub)], text=True, stderr=subprocess.DEVNULL).split("\n")
 start = [i for i, l in enumerate(sass) if l.startswith(".text.") and kern in l][0]
-seq, cur = [], None
+seq, cur, pending_reset = [], None, False
 for l in sass[start + 1:]:
     if l.startswith(".text.") and seq:
         break
-    m = re.search(r'//## File "([^"]+)", line (\d+)', l)
+    m = re.search(r'//## File "([^"]+)", line (\d+)(?: inlined at "([^"]+)", line (\d+))?', l)
     if m:
-        cur = (m.group(1).split("/")[-1], int(m.group(2)))
+        # CT_INLINE=1: header intrinsics (shuffles, __syncwarp) are attributed to the kernels.cuh line they were inlined at
+        if pending_reset:
+            cur = None; pending_reset = False
+        cand = (m.group(1).split("/")[-1], int(m.group(2)))
+        if cur is None or (not cur[0].endswith("kernels.cuh") and cand[0].endswith("kernels.cuh")):
+            cur = cand
+        if not cur[0].endswith("kernels.cuh") and m.group(3) and m.group(3).endswith("kernels.cuh"):
+            cur = (m.group(3).split("/")[-1], int(m.group(4)))
         continue
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
     if m:
         seq.append((int(m.group(1), 16), cur, m.group(2)))
+        pending_reset = True
 csvtxt = subprocess.check_output(["ncu", "-i", rep, "--page", "source", "--csv"], text=True, stderr=subprocess.DEVNULL)
 rows = list(csv.reader(csvtxt.split("\n")))
 hdr = rows[1]
