@@ -250,7 +250,10 @@ def main():
     b = make_batch(True)
     for _ in range(args.warmup):
         code = step_resident(b)
-    assert code >= 0, "integration failed with code %d" % code
+    if code < 0:
+        # per-reactor CVODE failure codes (CV_TOO_MUCH_WORK ...) are results, not errors: counted in "status" below; a
+        # library error (code <= -100) has already raised
+        print("bench: worst per-reactor status %d (see status.failed)" % code, file=sys.stderr)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -320,7 +323,7 @@ def main():
                          "traffic": ncu_traffic,
                          "flop_model": fm, "mean_counters": dict(zip(ctb.reactors.STAT_NAMES, st.mean(0).tolist()))},
             "clocks": clocks,
-            "status": {"failed": int((status < 0).sum()), "n": int(n)},
+            "status": {"failed": int((status < 0).sum()), "n": int(n), "max_steps": MAX_STEPS},
         }
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

@@ -88,6 +88,7 @@ def lib():
         "ct_batch_set_phase_alignment": (i32, [vp, i32]),
         "ct_batch_set_matrix_pool": (i32, [vp, i32, i32]),
         "ct_batch_set_time_slicing": (i32, [vp, i32]),
+        "ct_batch_set_alignment_period": (i32, [vp, i32]),
         "ct_batch_set_init_step": (i32, [vp, dbl]),
         "ct_batch_set_min_step": (i32, [vp, dbl]),
         "ct_batch_set_max_step": (i32, [vp, dbl]),
@@ -96,6 +97,8 @@ def lib():
         "ct_batch_set_max_conv_fails": (i32, [vp, i32]),
         "ct_batch_set_nonlin_conv_coef": (i32, [vp, dbl]),
         "ct_batch_reinit": (i32, [vp, dbl, vp]),
+        "ct_batch_set_trace": (i32, [vp, i64, i32]),
+        "ct_batch_get_trace": (i32, [vp, vp, vp]),
         "ct_batch_set_timeline": (i32, [vp, i32]),
         "ct_batch_get_timeline": (i32, [vp, vp]),
         "ct_batch_set_alignment_poll_ns": (i32, [vp, i32]),

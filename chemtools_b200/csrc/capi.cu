@@ -120,7 +120,7 @@ struct ct_batch {
   double t_start = 0.0; // integration start of a fresh batch (ct_batch_reinit)
   int max_order = 5, jac_mode = CT_JAC_ANALYTIC, ign_mode = 1, linsol = LINSOL_INVERSE;
   double ign_value = 400.0, jac_clip = 10.0;
-  int gang = 1, pool_enabled = 1, pool_n = 0, pool_warps = 12, gang_groups = 1, gang_sleep_ns = 200, gang_max_polls = 0;
+  int gang = 1, pool_enabled = 1, pool_n = 0, pool_warps = 12, gang_groups = 1, gang_sleep_ns = 200, gang_max_polls = 0, gang_period = 1;
   bool have_ic = false, fresh = true, roberts = false;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -129,6 +129,7 @@ struct ct_batch {
   DevBuf<int> status, order;
   DevBuf<unsigned long long> counter;
   DevBuf<long long> timeline; int timeline_on = 0;
+  DevBuf<double> trace; int trace_cap = 0; int64_t trace_reactor = -1;
   // time slicing (see BatchArgs): ring of reactor ids, per-reactor scratch
   DevBuf<int> ring, yielded; DevBuf<unsigned long long> ring_seq, qctl;
   int slice_steps = 64, ring_cap = 0; bool sliced = false;
@@ -179,7 +180,7 @@ int configure_launch(ct_batch* b) {
   b->grid = (int)std::max<int64_t>(1, std::min<int64_t>(di.sms, need));
   // time slicing needs the reactor-indexed scratch (49 KB per GRI-3.0 reactor): only while that stays below 4 GiB and
   // the batch is more than one wave of warps (otherwise nothing ever waits for a warp)
-  b->sliced = b->slice_steps > 0 && b->pool_n > 0 && b->n > (int64_t)b->grid * w &&
+  b->sliced = b->slice_steps > 0 && b->pool_n > 0 && b->trace_cap == 0 && b->n > (int64_t)b->grid * w &&
               (double)b->n * (double)warp_scratch_doubles(b->N, d.R) * 8.0 <= 4.0 * 1024 * 1024 * 1024;
   return 0;
 }
@@ -188,16 +189,17 @@ BatchArgs make_args(ct_batch* b) {
   BatchArgs a{};
   a.rt = b->roberts ? RT_ROBERTS : b->rt;
   a.N = b->N; a.jac_mode = b->jac_mode; a.max_order = b->max_order; a.ign_mode = b->ign_mode; a.fresh = b->fresh ? 1 : 0;
-  a.n_out = 0; a.n = b->n; a.mxstep = b->mxstep; a.linsol = b->linsol; a.jac_clip = b->jac_clip; a.gang = b->gang; a.pool_n = b->pool_n; a.gang_groups = b->gang_groups; a.gang_sleep_ns = b->gang_sleep_ns; a.gang_max_polls = b->gang_max_polls;
+  a.n_out = 0; a.n = b->n; a.mxstep = b->mxstep; a.linsol = b->linsol; a.jac_clip = b->jac_clip; a.gang = b->gang; a.pool_n = b->pool_n; a.gang_groups = b->gang_groups; a.gang_sleep_ns = b->gang_sleep_ns; a.gang_max_polls = b->gang_max_polls; a.gang_period = b->gang_period;
   a.T0 = b->pT0; a.p0 = b->pp0; a.rho0 = b->rho0.p;
   a.nt = b->nt; a.tab_t = b->tab_t.p; a.tab_T = b->tab_T.p; a.tab_p = b->tab_p.p;
   a.rtol = b->rtol; a.atol = b->atol; a.atol_vec = b->atol_vec.n ? b->atol_vec.p : nullptr;
   a.t_target = b->t_stop; a.t_stop = b->t_stop; a.ign_value = b->ign_value;
-  a.state = b->state.p; a.save = nullptr; a.save_stride = CT_LMAX * CT_NP + CT_SAVE_SCALARS; a.traj = nullptr;
+  a.state = b->state.p; a.save = nullptr; a.save_stride = CT_SAVE_DOUBLES; a.traj = nullptr;
   a.tau = b->tau.p; a.tcur = b->tcur.p; a.stats = b->stats.p; a.status = b->status.p; a.counter = b->counter.p;
   a.scratch = b->scratch.p; a.order = b->have_order ? b->order.p : nullptr;
   a.timeline = b->timeline_on ? b->timeline.p : nullptr;
   a.opts = b->opts; a.t_start = b->t_start;
+  if (b->trace_cap > 0) { a.trace = b->trace.p; a.trace_cap = b->trace_cap; a.trace_reactor = b->trace_reactor; }
   if (b->sliced) {
     a.slice_steps = b->slice_steps; a.ring_cap = b->ring_cap; a.ring = b->ring.p; a.ring_seq = b->ring_seq.p; a.qctl = b->qctl.p;
     a.yielded = b->yielded.p; a.save = b->save.p;
@@ -219,7 +221,7 @@ int ensure_runtime_buffers(ct_batch* b) {
   if (b->sliced) {
     b->ring_cap = (int)std::min<int64_t>(2 * b->n, 2147483647LL);
     CT_CUDA(b->ring.alloc(b->ring_cap)); CT_CUDA(b->ring_seq.alloc(b->ring_cap)); CT_CUDA(b->qctl.alloc(4)); CT_CUDA(b->yielded.alloc(b->n));
-    CT_CUDA(b->save.alloc((size_t)b->n * (CT_LMAX * CT_NP + CT_SAVE_SCALARS)));
+    CT_CUDA(b->save.alloc((size_t)b->n * (CT_SAVE_DOUBLES)));
   }
   CT_CUDA(b->tau.alloc(b->n)); CT_CUDA(b->tcur.alloc(b->n)); CT_CUDA(b->stats.alloc((size_t)b->n * 8));
   CT_CUDA(b->status.alloc(b->n)); CT_CUDA(b->counter.alloc(1));
@@ -613,6 +615,11 @@ int ct_batch_set_alignment_poll_ns(ct_batch* b, int ns) {
   b->gang_sleep_ns = ns;
   return 0;
 }
+int ct_batch_set_alignment_period(ct_batch* b, int period) {
+  if (!b || period < 1) return fail(CT_ERR_INVALID, "bad argument");
+  b->gang_period = period;
+  return 0;
+}
 int ct_batch_set_alignment_max_polls(ct_batch* b, int polls) {
   if (!b || polls < 0) return fail(CT_ERR_INVALID, "bad argument");
   b->gang_max_polls = polls;
@@ -621,6 +628,25 @@ int ct_batch_set_alignment_max_polls(ct_batch* b, int polls) {
 int ct_batch_set_time_slicing(ct_batch* b, int steps) {
   if (!b || steps < 0) return fail(CT_ERR_INVALID, "bad argument");
   b->slice_steps = steps;
+  return 0;
+}
+int ct_batch_set_trace(ct_batch* b, int64_t reactor, int capacity) {
+  if (!b || capacity < 0 || (capacity > 0 && (reactor < 0 || reactor >= b->n))) return fail(CT_ERR_INVALID, "bad trace arguments");
+  b->trace_cap = capacity; b->trace_reactor = reactor;
+  if (capacity > 0) {
+    CT_CUDA(b->trace.alloc((size_t)capacity * CT_TRACE_W + 1));
+    CT_CUDA(cudaMemset(b->trace.p, 0, ((size_t)capacity * CT_TRACE_W + 1) * sizeof(double)));
+  }
+  return 0;
+}
+int ct_batch_get_trace(ct_batch* b, double* out, int* count) {
+  if (!b || !out || !count) return fail(CT_ERR_INVALID, "null argument");
+  if (b->trace_cap <= 0) return fail(CT_ERR_INVALID, "step trace is off");
+  CT_CUDA(cudaStreamSynchronize(b->stream));
+  std::vector<double> h((size_t)b->trace_cap * CT_TRACE_W + 1);
+  CT_CUDA(cudaMemcpy(h.data(), b->trace.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  *count = (int)h.back();
+  std::memcpy(out, h.data(), (size_t)b->trace_cap * CT_TRACE_W * sizeof(double));
   return 0;
 }
 int ct_batch_set_timeline(ct_batch* b, int on) {

@@ -218,6 +218,9 @@ class ReactorBatch:
     def SetAlignmentPollNs(self, ns):
         check(lib().ct_batch_set_alignment_poll_ns(self._h, int(ns)))
 
+    def SetAlignmentPeriod(self, k):
+        check(lib().ct_batch_set_alignment_period(self._h, int(k)))
+
     def SetAlignmentMaxPolls(self, n):
         check(lib().ct_batch_set_alignment_max_polls(self._h, int(n)))
 
@@ -226,6 +229,16 @@ class ReactorBatch:
 
     def SetTimeSlicing(self, steps):
         check(lib().ct_batch_set_time_slicing(self._h, int(steps)))
+
+    def SetTrace(self, reactor, capacity=4096):
+        self._trace_cap = int(capacity)
+        check(lib().ct_batch_set_trace(self._h, int(reactor), int(capacity)))
+
+    def Trace(self):
+        """[count, 12] step-attempt records of the traced reactor (see ct_batch_set_trace)."""
+        out = np.zeros((self._trace_cap, 12)); cnt = C.c_int(0)
+        check(lib().ct_batch_get_trace(self._h, out.ctypes.data_as(C.c_void_p), C.byref(cnt)))
+        return out[:min(cnt.value, self._trace_cap)]
 
     def SetTimeline(self, on=True):
         check(lib().ct_batch_set_timeline(self._h, 1 if on else 0))

@@ -155,6 +155,7 @@ int ct_batch_set_jacobian_clip(ct_batch*, double thr);
  * share instruction fetches (the fused kernel is instruction-cache bound); default on */
 int ct_batch_set_phase_alignment(ct_batch*, int on); /* 0 off, 1 one group per CTA (default), 2 two groups (even/odd warps) */
 int ct_batch_set_alignment_poll_ns(ct_batch*, int ns); /* sleep between polls of the alignment barrier, default 200 */
+int ct_batch_set_alignment_period(ct_batch*, int period); /* meet at every period-th Newton residual; default 1 */
 int ct_batch_set_alignment_max_polls(ct_batch*, int polls); /* bounded wait: give up after that many polls; 0 = unbounded */
 /* scheduling only: keep the N x N Newton matrix out of the per-warp shared-memory slab (shared pool of work slabs for
  * Jacobian assembly + inversion, inverse parked in L2-resident global scratch) so that warps_per_sm (default 12)
@@ -165,6 +166,11 @@ int ct_batch_set_matrix_pool(ct_batch*, int on, int warps_per_sm);
  * reactors of the batch advance together and no warp idles while late starters finish.  Applies with the matrix pool
  * when the batch exceeds one wave of warps and the reactor-indexed scratch fits 4 GiB.  Default 64; 0 = off */
 int ct_batch_set_time_slicing(ct_batch*, int steps);
+/* solver diagnostics: one record of 12 doubles per step ATTEMPT of one reactor (nst, t, h, q, Newton flag, error-test
+ * flag, dsm, acnrm, component with the largest weighted correction, that correction, its predicted value,
+ * 100 * convergence failures + error-test failures of the step); turns time slicing off for the batch */
+int ct_batch_set_trace(ct_batch*, int64_t reactor, int capacity);
+int ct_batch_get_trace(ct_batch*, double* out /* capacity x 12 */, int* count);
 /* scheduling diagnostics: record per reactor [start ns, end ns (GPU global timer), sm * 64 + warp] during Integrate */
 int ct_batch_set_timeline(ct_batch*, int on);
 int ct_batch_get_timeline(ct_batch*, int64_t* out /* n x 3 */);

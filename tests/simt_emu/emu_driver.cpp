@@ -112,7 +112,7 @@ int emu_integrate(void* mv, int rt, long long n, const double* T0, const double*
   a.nt = nt; a.tab_t = tab_t; a.tab_T = tab_T; a.tab_p = tab_p;
   a.ign_value = ign_value; a.state = state; a.traj = traj; a.tau = tau; a.tcur = tcur.data(); a.stats = stats; a.status = status;
   a.counter = &counter; a.scratch = scratch.data(); a.linsol = linsol; a.jac_clip = jac_clip; a.gang = 1; a.pool_n = pool_n;
-  a.save_stride = CT_LMAX * CT_NP + CT_SAVE_SCALARS;
+  a.save_stride = CT_SAVE_DOUBLES;
   if (opts) {
     a.opts.h_init = opts[0]; a.opts.h_min = opts[1]; a.opts.h_max_inv = opts[2] > 0 ? 1.0 / opts[2] : 0.0; a.opts.nls_coef = opts[3];
     a.opts.max_nef = (int)opts[4]; a.opts.max_cor = (int)opts[5]; a.opts.max_ncf = (int)opts[6];

@@ -78,6 +78,11 @@ inline T emu_xchg(T v, int src) {
 }
 template <class T> inline T __shfl_sync(unsigned, T v, int src) { return emu_xchg(v, src); }
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_xchg(v, emu_lane ^ m); }
+inline int __any_sync(unsigned, int pred) {
+  int v = pred ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) v |= emu_xchg(v, emu_lane ^ o);
+  return v;
+}
 template <class T> inline T __shfl_down_sync(unsigned, T v, int d) { return emu_xchg(v, emu_lane + d < 32 ? emu_lane + d : emu_lane); }
 
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
