@@ -48,6 +48,8 @@ for r in data:
     k = s[1] if s else None
     n, sm = int(r[ci["Instructions Executed"]]), int(r[ci["# Samples"]])
     agg[k][0] += n; agg[k][1] += sm
+    if os.environ.get("CT_STALL"):  # samples of one stall reason instead of all samples
+        agg[k][1] += int(r[ci["stall_" + os.environ["CT_STALL"]]]) - sm
     for h in stalls:
         st_tot[h] += int(r[ci[h]])
     t = r[ci["Source"]].split()
