@@ -1,3 +1,4 @@
+"""Scan of the Jacobian clip threshold on a strided config-5 sample (the measurement behind DESIGN.md section 3, item 5)."""
 import sys, os, json, time
 import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
