@@ -44,3 +44,21 @@ def run(config_file, n_outputs=100, rtol=1e-9, atol=1e-15, max_num_steps=20000, 
                         write_case_hdf5(res["file"], res, energy_enabled=rtype <= Type.Const_Vol)
                     out.append(res)
     return out
+
+
+def main(argv=None):
+    """python -m chemtools_b200.app cases.yaml results_dir [n_outputs]"""
+    import sys
+    args = sys.argv[1:] if argv is None else argv
+    if len(args) < 2:
+        print(main.__doc__)
+        return 2
+    res = run(args[0], n_outputs=int(args[2]) if len(args) > 2 else 100, results_dir=args[1])
+    for r in res:
+        print("%-16s set %d case %d  status %d  steps %d  tau_ign %s" % (r["reactor"], r["case_set"], r["case"], r["status"],
+                                                                      int(r["statistics"][0]), "%.6e s" % r["ignition_delay"] if np.isfinite(r["ignition_delay"]) else "-"))
+    return 0 if all(r["status"] >= 0 for r in res) else 1
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())
