@@ -418,6 +418,26 @@ def test_solver_options_and_reinitialise(ctb, chem, omech):
         r.ReInitialise(2e-3, mid)  # start time beyond the stop time
 
 
+def test_retry_of_crawling_reactors(ctb, chem, omech):
+    """Reactors 11018, 11228, 44404 and 61433 of BASELINE config 3 (GRI-1.2, seed 20211) are the ones that ended with
+    CV_TOO_MUCH_WORK / CV_ERR_FAILURE in the full-size run of round 1 (tools/fullsize_probe.py); whichever of them
+    fail today, IntegrateWithRetry must bring every reactor to the stop time with the oracle's answer."""
+    from chemtools_b200 import workloads as W
+    ch, om = chem("gri12"), omech("gri12")
+    mech, rt, T0, p0, X, t_end, _ = W.config3(ch, "gri12", 65536, 20211)
+    sel = np.array([11018, 11228, 44404, 61433, 7, 8])
+    T0, p0, Y0 = T0[sel].copy(), p0[sel].copy(), ch.mass_fractions(X[sel])
+    b = ctb.ReactorBatch(rt, ch, T0, p0, Y0, 1e-8, 1e-14, t_end, max_num_steps=50000)
+    res = b.IntegrateWithRetry()
+    assert np.all(res["status"] >= 0)
+    ref = om.integrate_batch(int(rt), T0, p0, Y0, t_end, rtol=1e-8, atol=1e-14, max_steps=400000, nthreads=6)
+    assert np.all(ref["status"] >= 0)
+    assert np.abs(res["state"][:, 0] / ref["state"][:, 0] - 1).max() < TRAJ_TOL
+    ok = np.isfinite(ref["tau"])
+    assert np.array_equal(np.isfinite(res["ignition_delay"]), ok)
+    assert np.abs(res["ignition_delay"][ok] / ref["tau"][ok] - 1).max() < 5e-4
+
+
 def test_empty_and_error_paths(ctb, chem):
     ch = chem("gri30")
     b = ctb.ReactorBatch(0, ch, np.zeros(0), np.zeros(0), np.zeros((0, ch.n_species)))
