@@ -97,6 +97,8 @@ def lib():
         "ct_batch_set_max_conv_fails": (i32, [vp, i32]),
         "ct_batch_set_nonlin_conv_coef": (i32, [vp, dbl]),
         "ct_batch_reinit": (i32, [vp, dbl, vp]),
+        "ct_batch_set_max_warn_messages": (i32, [vp, i32]),
+        "ct_batch_set_stability_limit_detection": (i32, [vp, i32]),
         "ct_batch_set_trace": (i32, [vp, i64, i32]),
         "ct_batch_get_trace": (i32, [vp, vp, vp]),
         "ct_batch_set_timeline": (i32, [vp, i32]),

@@ -576,6 +576,19 @@ int ct_batch_set_nonlin_conv_coef(ct_batch* b, double c) {
   b->opts.nls_coef = c;
   return 0;
 }
+// IStrategy::SetMaxWarnMessages (interface.cpp:125-137): CVODE's "t + h = t" warnings are not printed by the device
+// stepper, the count is validated and otherwise ignored.  IStrategy::SetStabilityLimitDetection (interface.cpp:139-164):
+// the BDF stability-limit detection algorithm is not implemented; switching it on is refused instead of ignored.
+int ct_batch_set_max_warn_messages(ct_batch* b, int n) {
+  if (!b) return fail(CT_ERR_INVALID, "null batch");
+  if (n < 0) return fail(CT_ILL_INPUT, "SetMaxWarnMessages: must be non-negative");
+  return 0;
+}
+int ct_batch_set_stability_limit_detection(ct_batch* b, int on) {
+  if (!b) return fail(CT_ERR_INVALID, "null batch");
+  if (on) return fail(CT_ERR_UNSUPPORTED, "stability limit detection (CVodeSetStabLimDet) is not implemented");
+  return 0;
+}
 // IStrategy::ReInitialise(time_init, state) (interface.cpp:429-446) -> CVodeReInit: new start time and state, all
 // options, tolerances and the reactors' frozen parameters (pressure / density of the original initial conditions) kept
 int ct_batch_reinit(ct_batch* b, double t0, const double* state) {

@@ -199,6 +199,12 @@ class ReactorBatch:
     def SetNonlinConvergenceCoefficient(self, c):
         check(lib().ct_batch_set_nonlin_conv_coef(self._h, float(c)))
 
+    def SetMaxWarnMessages(self, n):
+        check(lib().ct_batch_set_max_warn_messages(self._h, int(n)))
+
+    def SetStabilityLimitDetection(self, on):
+        check(lib().ct_batch_set_stability_limit_detection(self._h, 1 if on else 0))
+
     def ReInitialise(self, time_init, state):
         """IStrategy::ReInitialise (interface.cpp:429-446): restart from state[n, N] at time_init."""
         st = _f64(np.atleast_2d(state))

@@ -136,6 +136,10 @@ int ct_batch_set_max_err_test_fails(ct_batch*, int n);
 int ct_batch_set_max_nonlin_iters(ct_batch*, int n);
 int ct_batch_set_max_conv_fails(ct_batch*, int n);
 int ct_batch_set_nonlin_conv_coef(ct_batch*, double coef);
+/* SetMaxWarnMessages: validated (>= 0), no effect (the device stepper prints nothing).  SetStabilityLimitDetection:
+ * only `off` (the reference's default, types.hpp:99) is supported, `on` returns CT_ERR_UNSUPPORTED */
+int ct_batch_set_max_warn_messages(ct_batch*, int n);
+int ct_batch_set_stability_limit_detection(ct_batch*, int on);
 /* IStrategy::ReInitialise(time_init, state) (interface.cpp:429-446): restart every reactor from state[n x N] at t0,
  * keeping options, tolerances and the frozen reactor parameters of the original initial conditions */
 int ct_batch_reinit(ct_batch*, double t0, const double* state);

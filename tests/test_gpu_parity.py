@@ -397,6 +397,11 @@ def test_solver_options_and_reinitialise(ctb, chem, omech):
                       (b.SetMaxNonlinearIterations, 0), (b.SetMaxConvergenceFailures, -2), (b.SetNonlinConvergenceCoefficient, 0.0)):
         with pytest.raises(ctb.reactors.CtError):
             call(bad)
+    b.SetMaxWarnMessages(3); b.SetStabilityLimitDetection(False)
+    with pytest.raises(ctb.reactors.CtError):
+        b.SetMaxWarnMessages(-1)
+    with pytest.raises(ctb.reactors.CtError):
+        b.SetStabilityLimitDetection(True)  # not implemented: refused, not ignored
     # minimum step too large for the ignition front: CVODE's failure class per reactor, same as the oracle
     refm = om.integrate_batch(1, T0, p0, Y0, 1e-3, rtol=1e-8, atol=1e-14, max_steps=50000, options=dict(min_step=2e-6), nthreads=8)
     bm = ctb.ReactorBatch(1, ch, T0, p0, Y0, 1e-8, 1e-14, 1e-3, max_num_steps=50000)
