@@ -40,7 +40,8 @@ std::string canon_element(const std::string& e) {
 }  // namespace
 
 CompiledMech compile_mechanism(const MechanismDef& D, const std::string& constants_name) {
-  const ConstantSet& cs = constant_set(constants_name.empty() ? kDefaultConstants : constants_name);
+  const std::string cname = constants_name.empty() ? std::string(kDefaultConstants) : constants_name;
+  const ConstantSet& cs = constant_set(cname);
   if (D.u_length != "cm" || D.u_quantity != "mol" || D.u_act_energy != "cal/mol" || D.u_time != "s")
     throw MechError("unsupported CTI unit system (only length=cm, time=s, quantity=mol, act_energy=cal/mol)");
   CompiledMech C;
