@@ -443,6 +443,74 @@ def test_retry_of_crawling_reactors(ctb, chem, omech):
     assert np.abs(res["ignition_delay"][ok] / ref["tau"][ok] - 1).max() < 5e-4
 
 
+@pytest.mark.parametrize("mech", ["gri12", "gri211"])
+def test_config3_full_size_properties(ctb, chem, mech):
+    """BASELINE config 3 at full size (65 536 constant-pressure CH4/air reactors, randomised T0 / p / phi): mass
+    fractions sum to one, element mass and (constant pressure, adiabatic) specific enthalpy are conserved, and at most
+    0.2 % of the reactors end with a negative CVODE status (the crawl of DESIGN.md section 3 item 5, which the reference's
+    algorithm shows at the same rate)."""
+    from chemtools_b200 import workloads as W
+    ch = chem(mech)
+    _, rt, T0, p0, X, t_end, _ = W.config3(ch, mech, 65536, 20211)
+    Y0 = ch.mass_fractions(X)
+    b = ctb.ReactorBatch(rt, ch, T0, p0, Y0, 1e-8, 1e-14, t_end, max_num_steps=50000)
+    b.Integrate(t_end)
+    status = b.Status()
+    ok = status >= 0
+    assert (~ok).mean() <= 0.002
+    Y = b.MassFractions()[ok]
+    assert np.abs(Y.sum(1) - 1).max() < 1e-7
+    Wk = ch.getMolecularWeights()
+    nel = len(ch.elements())
+    A = np.array([[ch.nAtoms(k, e) for e in range(nel)] for k in range(ch.n_species)])
+    el0, el1 = (Y0[ok] / Wk) @ A, (Y / Wk) @ A
+    assert np.abs(el1 - el0).max() / np.abs(el0).max() < 1e-7
+    assert np.allclose(b.Time()[ok], t_end)
+    T = b.Temperature()[ok]
+    assert T.min() > 900.0 and T.max() < 3500.0 and (T > T0[ok] + 400).mean() > 0.3  # a good part has ignited
+
+
+def test_config4_and_config5_large_slices(ctb, chem):
+    """BASELINE config 4 (prescribed T(t), p(t), first 32 768 of the 262 144 reactors) and config 5 (a 16 384-reactor
+    strided slice of the 256^3 constant-pressure map): conservation properties, failure rate, and for the map the
+    ignition delay falling with T0 along lines of constant p and phi."""
+    from chemtools_b200 import workloads as W
+    ch = chem("gri30")
+    Wk = ch.getMolecularWeights()
+    nel = len(ch.elements())
+    A = np.array([[ch.nAtoms(k, e) for e in range(nel)] for k in range(ch.n_species)])
+    _, rt, Ta, pa, X, t_end, extra = W.config4(ch, 32768, 101, 30)
+    Y0 = ch.mass_fractions(X)
+    b = ctb.ReactorBatch(rt, ch, Ta, pa, Y0, 1e-8, 1e-14, t_end, max_num_steps=50000)
+    b.SetTable(*extra["table"])
+    b.Integrate(t_end)
+    ok = b.Status() >= 0
+    assert (~ok).mean() <= 0.002
+    Y = b.MassFractions()[ok]
+    assert np.abs(Y.sum(1) - 1).max() < 1e-7
+    el0, el1 = (Y0[ok] / Wk) @ A, (Y / Wk) @ A
+    assert np.abs(el1 - el0).max() / np.abs(el0).max() < 1e-7
+    assert (Y[:, ch.speciesIndex("CH4")] < 0.5 * Y0[ok][:, ch.speciesIndex("CH4")]).mean() > 0.5  # heated to 1500-2200 K: fuel consumed
+    # config 5: 32 T0 values x 512 (p, phi) pairs
+    iT = np.repeat(np.arange(0, 256, 8), 512)
+    rng = np.random.default_rng(5)
+    ip, iphi = np.tile(rng.integers(0, 256, 512), 32), np.tile(rng.integers(0, 256, 512), 32)
+    T0 = np.linspace(1000.0, 2000.0, 256)[iT]; p0 = np.geomspace(1.0, 40.0, 256)[ip] * W.ONE_ATM
+    phi = np.linspace(0.5, 2.0, 256)[iphi]
+    Y0 = ch.mass_fractions(W._fill(ch, len(T0), {"CH4": phi, "O2": 2.0, "N2": 7.52}))
+    c = ctb.ReactorBatch(ctb.Type.Const_Pres, ch, T0, p0, Y0, 1e-8, 1e-14, 1e-3, max_num_steps=50000)
+    c.Integrate(1e-3)
+    ok = c.Status() >= 0
+    assert (~ok).mean() <= 0.002
+    Y = c.MassFractions()
+    assert np.abs(Y[ok].sum(1) - 1).max() < 1e-7
+    el0, el1 = (Y0[ok] / Wk) @ A, (Y[ok] / Wk) @ A
+    assert np.abs(el1 - el0).max() / np.abs(el0).max() < 1e-7
+    tau = np.where(ok, c.IgnitionDelay(), np.nan).reshape(32, 512)
+    both = np.isfinite(tau[:-1]) & np.isfinite(tau[1:])
+    assert both.sum() > 2000 and (tau[1:][both] < tau[:-1][both]).mean() > 0.995  # hotter ignites earlier
+
+
 def test_empty_and_error_paths(ctb, chem):
     ch = chem("gri30")
     b = ctb.ReactorBatch(0, ch, np.zeros(0), np.zeros(0), np.zeros((0, ch.n_species)))
