@@ -14,5 +14,9 @@ Y = chem.mass_fractions(W._fill(chem, n, {"CH4": phi, "O2": 2.0, "N2": 7.52}))
 for c in json.loads(os.environ.get("CASES", '[{"w":12},{"w":10},{"w":11}]')):
     b = ctb.ReactorBatch(ctb.Type.Const_Pres, chem, T0, p0, Y, 1e-8, 1e-14, 1e-3, max_num_steps=50000)
     b.SetMatrixPool(1, c.get("w", 0))
+    if "slice" in c: b.SetTimeSlicing(c["slice"])
+    if "clip" in c: b.SetJacobianClip(c["clip"])
+    if "ns" in c: b.SetAlignmentPollNs(c["ns"])
     code = b.Integrate(1e-3)
-    print(json.dumps(dict(**c, code=int(code), wpb=b.WarpsPerSM(), kernel_ms=round(b.LastKernelMs(), 1), reactors_per_s=round(n / b.LastKernelMs() * 1e3))), flush=True)
+    st = b.Statistics()
+    print(json.dumps(dict(**c, nst=int(st[:, 0].mean()), nsetups=int(st[:, 2].mean()), maxnst=int(st[:, 0].max()), code=int(code), wpb=b.WarpsPerSM(), kernel_ms=round(b.LastKernelMs(), 1), reactors_per_s=round(n / b.LastKernelMs() * 1e3))), flush=True)
