@@ -73,11 +73,15 @@ CompiledMech compile_mechanism(const MechanismDef& D, const std::string& constan
         if (canon_element(D.elements[e]) == el) C.natoms[k * D.elements.size() + e] = a.second;
     }
   }
-  // device order: falloff | three-body | elementary  (stable within each class)
-  for (int pass = 0; pass < 3; ++pass)
+  // device order: falloff | three-body | elementary with a temperature-dependent k_f | elementary with b = 0 and
+  // Ea = 0 (k_f = A: Cantera's A exp(0) is exactly A, so whole lane-passes over that tail skip the exponential);
+  // stable within each class
+  for (int pass = 0; pass < 4; ++pass)
     for (int i = 0; i < R; ++i) {
-      RxnKind want = pass == 0 ? RxnKind::Falloff : pass == 1 ? RxnKind::ThreeBody : RxnKind::Elementary;
-      if (D.reactions[i].kind == want) C.perm.push_back(i);
+      const ReactionDef& r = D.reactions[i];
+      const bool constant = r.kind == RxnKind::Elementary && r.kf[1] == 0.0 && r.kf[2] == 0.0;
+      const int cls = r.kind == RxnKind::Falloff ? 0 : r.kind == RxnKind::ThreeBody ? 1 : constant ? 3 : 2;
+      if (cls == pass) { C.perm.push_back(i); if (constant) C.n_const++; }
     }
   C.inv_perm.assign(R, 0);
   for (int d = 0; d < R; ++d) C.inv_perm[C.perm[d]] = d;
