@@ -60,7 +60,7 @@ struct DevBuf {
 
 MechDesc make_desc(const CompiledMech& C) {
   MechDesc d{};
-  d.K = C.K; d.R = C.R; d.nf = C.n_fall; d.n3 = C.n_3b; d.KP = C.KP; d.nc = C.n_const; d.Rgas = C.gas_constant; d.p_ref = C.p_ref;
+  d.K = C.K; d.R = C.R; d.nf = C.n_fall; d.n3 = C.n_3b; d.KP = C.KP; d.nc = C.n_const; d.Rgas = C.gas_constant; d.p_ref = C.p_ref; d.kc_Tmin = C.kc_fast_Tmin;
   const auto& o = C.off;
   d.o_W = o.W; d.o_rW = o.rW; d.o_Tmid = o.Tmid; d.o_nasa = o.nasa; d.o_A = o.A; d.o_b = o.b; d.o_E = o.E; d.o_A0 = o.A0;
   d.o_b0 = o.b0; d.o_E0 = o.E0; d.o_ta = o.troe_a; d.o_rt3 = o.troe_rt3; d.o_rt1 = o.troe_rt1; d.o_t2 = o.troe_t2;

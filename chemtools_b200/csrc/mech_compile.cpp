@@ -187,6 +187,24 @@ CompiledMech compile_mechanism(const MechanismDef& D, const std::string& constan
     sp_ptr[k + 1] = (int)sp_rxn.size();
   }
   auto& o = C.off;
+  // Range check for the per-species form of 1/Kc (kernels.cuh: recip_kc): the product of three exp(+-mu0/RT) must stay
+  // inside the fp64 range, i.e. |g0/RT| + |ln(p/p_ref)| (<= 10 up to 2e4 atm) below 230 for every species.  g0/RT falls
+  // in magnitude with T, so the lowest temperature that passes is searched from 400 K upwards.
+  {
+    auto g_rt = [](const double* a, double T) {
+      return a[0] * (1.0 - std::log(T)) - a[1] * T / 2.0 - a[2] * T * T / 6.0 - a[3] * T * T * T / 12.0 - a[4] * T * T * T * T / 20.0 + a[5] / T - a[6];
+    };
+    double Tmin = 400.0;
+    for (; Tmin < 3000.0; Tmin += 100.0) {
+      double worst = 0.0;
+      for (int k = 0; k < K; ++k) {
+        const SpeciesDef& sp = D.species[k];
+        worst = std::max(worst, std::fabs(g_rt(Tmin <= sp.Tmid ? sp.a_lo : sp.a_hi, Tmin)));
+      }
+      if (worst + 10.0 < 230.0) break;
+    }
+    C.kc_fast_Tmin = Tmin;
+  }
   o.W = append(C.blob, C.W); o.rW = append(C.blob, rW); o.Tmid = append(C.blob, Tmid); o.nasa = append(C.blob, nasa);
   o.A = append(C.blob, A); o.b = append(C.blob, b); o.E = append(C.blob, E);
   o.A0 = append(C.blob, A0); o.b0 = append(C.blob, b0); o.E0 = append(C.blob, E0);

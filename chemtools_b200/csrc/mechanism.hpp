@@ -70,6 +70,7 @@ extern const char* const kDefaultConstants;
 // Device reaction order: [falloff | three-body | elementary]; perm[d] = file index.
 struct CompiledMech {
   int K = 0, R = 0, n_fall = 0, n_3b = 0, KP = 64;
+  double kc_fast_Tmin = 400.0;  // above this temperature 1/Kc may be formed from per-species factors exp(mu0/RT) (range check)
   int n_const = 0;  // trailing elementary reactions with b = 0 and Ea = 0 (k_f = A exactly: no exponential needed)
   double gas_constant = 0, p_ref = 0;
   std::string constants;
