@@ -24,6 +24,7 @@ def _cloud(om, n, seed, fuel=None):
     Y[:, om.index["N2"]] += 1.0
     Y /= Y.sum(1, keepdims=True)
     T = rng.uniform(700.0, 3000.0, n)
+    T[: n // 8] = rng.uniform(250.0, 430.0, n // 8)  # cold states: Cantera's own 1/Kc arithmetic below 400 K (recip_kc)
     p = np.exp(rng.uniform(np.log(0.3), np.log(40.0), n)) * 101325.0
     return T, p, Y, rng
 
