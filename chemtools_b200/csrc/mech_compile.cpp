@@ -242,19 +242,26 @@ CompiledMech compile_mechanism(const MechanismDef& D, const std::string& constan
       while (i < flat[k].size()) {
         const size_t room = chunk - (pos % chunk);
         const size_t len = std::min(room, flat[k].size() - i);
-        pstart.push_back((unsigned short)ent.size());
+        // entries are byte offsets into the per-warp q[] array (reaction index * 8), stored in PAIRS (one 32-bit load
+        // per two terms); an odd run is padded with the offset of q[R], a slot that is never written and stays zero
+        pstart.push_back((unsigned short)(ent.size() / 2));
         piece_lane.push_back((int)(pos / chunk));
+        const unsigned short zero_slot = (unsigned short)(8 * R);
         unsigned short np = 0;
-        for (size_t j = i; j < i + len; ++j) if (flat[k][j].second > 0) { ent.push_back((unsigned short)flat[k][j].first); ++np; }
-        for (size_t j = i; j < i + len; ++j) if (flat[k][j].second < 0) ent.push_back((unsigned short)flat[k][j].first);
-        pnplus.push_back(np);
+        for (size_t j = i; j < i + len; ++j) if (flat[k][j].second > 0) { ent.push_back((unsigned short)(8 * flat[k][j].first)); ++np; }
+        if (np & 1) { ent.push_back(zero_slot); ++np; }
+        unsigned short nm = 0;
+        for (size_t j = i; j < i + len; ++j) if (flat[k][j].second < 0) { ent.push_back((unsigned short)(8 * flat[k][j].first)); ++nm; }
+        if (nm & 1) ent.push_back(zero_slot);
+        pnplus.push_back((unsigned short)(np / 2));
         i += len; pos += len;
       }
     }
     spp[K] = (unsigned char)pstart.size();
     const int P = (int)pstart.size();
     if (P > 128 || P > 250) throw MechError("too many gather pieces for the shared partial buffer");
-    pstart.push_back((unsigned short)ent.size());
+    pstart.push_back((unsigned short)(ent.size() / 2));
+    if (8 * (R + 1) > 65535) throw MechError("too many reactions for 16-bit gather offsets");
     for (int l = 0; l <= 32; ++l) {
       int first = P;
       for (int pc = P - 1; pc >= 0; --pc) if (piece_lane[pc] >= l) first = pc;
