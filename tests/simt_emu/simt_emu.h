@@ -106,7 +106,7 @@ void emu_launch(Kernel k, unsigned grid, unsigned block, size_t smem_bytes, Args
     blk.bar.reset((int)block);
     blk.warps = std::vector<EmuWarp>((block + 31) / 32);
     for (unsigned w = 0; w < blk.warps.size(); ++w) blk.warps[w].bar.reset((int)std::min(32u, block - 32 * w));
-    std::vector<unsigned char> smem(smem_bytes + 64);
+    std::vector<unsigned char> smem(smem_bytes + 64, 0xFF);  // NaN pattern: real shared memory is NOT zero-initialised
     blk.smem = (unsigned char*)(((uintptr_t)smem.data() + 63) & ~(uintptr_t)63);
     std::vector<std::thread> th;
     for (unsigned t = 0; t < block; ++t) {
