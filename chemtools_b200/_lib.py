@@ -122,6 +122,7 @@ def lib():
         "ct_jacobian_eval": (i32, [vp, i32, dp, dp, dp]),
         "ct_lu_solve": (i32, [i32, i64, dp, dp, dp, ip, i32]),
         "ct_rhs_time": (i32, [vp, dp, i32, dp]),
+        "ct_rhs_time_cfg": (i32, [vp, dp, i32, i32, i32, dp]),
         "ct_jacobian_time": (i32, [vp, i32, dp, i32, dp]),
         "ct_lu_time": (i32, [i32, i64, i32, i32, i32, dp]),
         "ct_measure_fp64_peak": (i32, [dp]),

@@ -862,6 +862,51 @@ int ct_rhs_time(ct_batch* b, const double* states, int reps, double* ms) {
   return 0;
 }
 
+// occupancy scan of K1 for the roofline report: the right-hand side in the fused kernel's slab layout (no Newton matrix in
+// the per-warp slab), `warps_per_block` warps per CTA and `blocks_per_sm` CTAs per SM under the matching register cap
+int ct_rhs_time_cfg(ct_batch* b, const double* states, int reps, int warps_per_block, int blocks_per_sm, double* ms) {
+  if (!b || !states || !ms || reps < 1 || warps_per_block < 1 || warps_per_block > 32 || blocks_per_sm < 1) return fail(CT_ERR_INVALID, "bad argument");
+  if (!b->have_ic) return fail(CT_ILL_INPUT, "initial conditions not set");
+  DeviceInfo di;
+  if (int r = device_info(di)) return r;
+  const unsigned char* blob; const int* perm;
+  if (int r = b->mech->on_device(&blob, &perm)) return r;
+  const WarpLayout L = make_layout(b->N, b->mech->desc.R, false);
+  const size_t smem = CT_HDR_BYTES + b->mech->desc.blob_bytes + (size_t)warps_per_block * L.doubles * sizeof(double);
+  if (smem > (size_t)di.max_smem_optin) return fail(CT_ERR_UNSUPPORTED, "too many warps per block for one SM's shared memory");
+  const size_t nN = (size_t)b->n * b->N;
+  CT_CUDA(b->tmp_in.alloc(nN)); CT_CUDA(b->tmp_out.alloc(nN)); CT_CUDA(b->tmp_w.alloc((size_t)b->n * b->K));
+  CT_CUDA(cudaMemcpy(b->tmp_in.p, states, nN * sizeof(double), cudaMemcpyHostToDevice));
+  if (!b->ev0) { CT_CUDA(cudaEventCreate(&b->ev0)); CT_CUDA(cudaEventCreate(&b->ev1)); }
+  BatchArgs a = make_args(b);
+  a.pool_n = 1;  // slab without the matrix
+  const int threads = warps_per_block * 32, grid = di.sms * blocks_per_sm;
+  auto launch = [&]() {
+    if (threads <= 256) k_rhs_t<256><<<grid, threads, smem, b->stream>>>(b->mech->desc, blob, a, b->tmp_in.p, nullptr, b->tmp_out.p, b->tmp_w.p, nullptr, nullptr, perm);
+    else if (threads <= 384) k_rhs_t<384><<<grid, threads, smem, b->stream>>>(b->mech->desc, blob, a, b->tmp_in.p, nullptr, b->tmp_out.p, b->tmp_w.p, nullptr, nullptr, perm);
+    else if (threads <= 512) k_rhs_t<512><<<grid, threads, smem, b->stream>>>(b->mech->desc, blob, a, b->tmp_in.p, nullptr, b->tmp_out.p, b->tmp_w.p, nullptr, nullptr, perm);
+    else if (threads <= 768) k_rhs_t<768><<<grid, threads, smem, b->stream>>>(b->mech->desc, blob, a, b->tmp_in.p, nullptr, b->tmp_out.p, b->tmp_w.p, nullptr, nullptr, perm);
+    else k_rhs_t<1024><<<grid, threads, smem, b->stream>>>(b->mech->desc, blob, a, b->tmp_in.p, nullptr, b->tmp_out.p, b->tmp_w.p, nullptr, nullptr, perm);
+  };
+  if (int r = set_smem(k_rhs_t<256>, smem)) return r;
+  if (int r = set_smem(k_rhs_t<384>, smem)) return r;
+  if (int r = set_smem(k_rhs_t<512>, smem)) return r;
+  if (int r = set_smem(k_rhs_t<768>, smem)) return r;
+  if (int r = set_smem(k_rhs_t<1024>, smem)) return r;
+  for (int w = 0; w < 3; ++w) launch();
+  CT_CUDA(cudaGetLastError());
+  CT_CUDA(cudaEventRecord(b->ev0, b->stream));
+  for (int w = 0; w < reps; ++w) launch();
+  CT_CUDA(cudaEventRecord(b->ev1, b->stream));
+  CT_CUDA(cudaStreamSynchronize(b->stream));
+  CT_CUDA(cudaGetLastError());
+  float t = 0.f;
+  CT_CUDA(cudaEventElapsedTime(&t, b->ev0, b->ev1));
+  *ms = t / reps;
+  b->launches += reps + 3;
+  return 0;
+}
+
 static int jac_launch(ct_batch* b, int mode, const double* d_states, const double* d_times, double* d_J, int reps, double* ms) {
   int wpb, grid; size_t smem;
   if (int r = standalone_cfg(b, &wpb, &grid, &smem, true)) return r;

@@ -420,6 +420,12 @@ class ReactorBatch:
         check(lib().ct_rhs_time(self._h, _p(_f64(states)), reps, C.cast(C.byref(ms), dp)))
         return ms.value
 
+    def time_rhs_cfg(self, states, warps_per_block, blocks_per_sm, reps=20):
+        """K1 in the fused kernel's slab layout at a chosen occupancy (ms per launch)."""
+        ms = C.c_double()
+        check(lib().ct_rhs_time_cfg(self._h, _p(_f64(states)), reps, int(warps_per_block), int(blocks_per_sm), C.cast(C.byref(ms), dp)))
+        return ms.value
+
     def time_jacobian(self, states, mode="analytic", reps=5):
         ms = C.c_double()
         check(lib().ct_jacobian_time(self._h, {"dq": 0, "analytic": 1}[mode], _p(_f64(states)), reps, C.cast(C.byref(ms), dp)))

@@ -219,6 +219,8 @@ int ct_jacobian_eval(ct_batch*, int mode, const double* states, const double* ti
 int ct_lu_solve(int N, int64_t n, const double* A, const double* b, double* x, int32_t* info, int linsol);
 /* timing loops for the roofline report: run the kernel `reps` times on resident data, return mean ms per launch */
 int ct_rhs_time(ct_batch*, const double* states, int reps, double* ms);
+/* K1 in the fused kernel's slab layout with warps_per_block warps per CTA and blocks_per_sm CTAs per SM (occupancy scan) */
+int ct_rhs_time_cfg(ct_batch*, const double* states, int reps, int warps_per_block, int blocks_per_sm, double* ms);
 int ct_jacobian_time(ct_batch*, int mode, const double* states, int reps, double* ms);
 int ct_lu_time(int N, int64_t n, int reps, int solves_per_factor, int linsol, double* ms);
 /* measured fp64 FMA peak of the current device in TFLOP/s (register-resident DFMA loop) */

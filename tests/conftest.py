@@ -22,6 +22,13 @@ def goldens():
 
 
 @pytest.fixture(scope="session")
+def config5_golden():
+    """Oracle results on the 128-reactor design over BASELINE config 5 (tools/make_config5_golden.py)."""
+    import numpy as np
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "config5_oracle.npz")))
+
+
+@pytest.fixture(scope="session")
 def oracle():
     from oracle import oracle as O
     O.lib()

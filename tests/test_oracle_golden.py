@@ -149,3 +149,36 @@ def test_oracle_against_scipy_bdf(omech):
     sol = solve_ivp(f, (0, t_end), np.concatenate([[T0], Y0]), method="LSODA", rtol=1e-10, atol=1e-16)
     assert sol.success
     assert abs(sol.y[0, -1] / r["state"][0, 0] - 1) < 1e-6
+
+
+def test_config5_fixture_is_the_oracle(omech, config5_golden):
+    """tests/golden/config5_oracle.npz (the fixture the GPU tier compares the north-star workload with) is what
+    oracle/ produces: the design is re-generated and the 1e-9/1e-15 and 1e-11/1e-17 runs are repeated here (the
+    1e-8/1e-14 run holds one crawling reactor of 200 000 steps and is only checked for internal consistency)."""
+    import importlib.util
+    import os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("make_config5_golden", os.path.join(ROOT, "tools", "make_config5_golden.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    g = config5_golden
+    idx = mk.design(128)
+    assert np.array_equal(idx, g["idx"])
+    T0, p0, phi = mk.conditions(idx)
+    assert np.array_equal(T0, g["T0"]) and np.array_equal(p0, g["p0"]) and np.array_equal(phi, g["phi"])
+    assert T0.min() == 1000.0 and T0.max() == 2000.0 and phi.min() == 0.5 and phi.max() == 2.0
+    assert abs(p0.min() / 101325.0 - 1) < 1e-12 and abs(p0.max() / 101325.0 / 40.0 - 1) < 1e-12
+    m = omech("gri30")
+    sub = np.arange(0, 128, 4)  # every 4th reactor keeps the CPU tier short
+    for tag, rtol, atol in (("ref", 1e-9, 1e-15), ("tight", 1e-11, 1e-17)):
+        r = m.integrate_batch("Const_Pres", T0[sub], p0[sub], g["Y0"][sub], 1e-3, rtol=rtol, atol=atol, max_steps=200000, nthreads=8)
+        assert np.array_equal(r["status"], g["status_" + tag][sub])
+        assert np.array_equal(r["stats"], g["stats_" + tag][sub])
+        assert np.array_equal(r["state"], g["state_" + tag][sub])
+        assert np.array_equal(r["tau"], g["tau_" + tag][sub], equal_nan=True)
+    ign = np.isfinite(g["tau_tight"])
+    ok = g["status_head"] >= 0
+    assert ign.sum() >= 64 and (~ok).sum() <= 1
+    for tag in ("ref", "head"):
+        assert np.abs(g["tau_" + tag][ign & ok] / g["tau_tight"][ign & ok] - 1).max() < 1e-6
+        assert np.abs(g["state_" + tag][ok, 0] / g["state_tight"][ok, 0] - 1).max() < 1e-6
