@@ -86,6 +86,8 @@ def lib():
         "ct_batch_set_linear_solver": (i32, [vp, i32]),
         "ct_batch_set_jacobian_clip": (i32, [vp, dbl]),
         "ct_batch_set_phase_alignment": (i32, [vp, i32]),
+        "ct_batch_set_static_shape": (i32, [vp, i32]),
+        "ct_mech_static_shape": (i32, [vp]),
         "ct_batch_set_matrix_pool": (i32, [vp, i32, i32]),
         "ct_batch_set_time_slicing": (i32, [vp, i32]),
         "ct_batch_set_alignment_period": (i32, [vp, i32]),
@@ -108,6 +110,9 @@ def lib():
         "ct_batch_set_tp_table": (i32, [vp, i32, dp, dp, dp]),
         "ct_batch_set_order": (i32, [vp, ip]),
         "ct_batch_integrate": (i32, [vp, dbl]),
+        "ct_batch_integrate_with_retry": (i32, [vp, lp, lp]),
+        "ct_batch_get_stats_ex": (i32, [vp, dp]),
+        "ct_batch_set_tolerances_vec": (i32, [vp, dbl, dp]),
         "ct_batch_integrate_trajectory": (i32, [vp, i32, dp]),
         "ct_batch_get_state": (i32, [vp, dp]),
         "ct_batch_get_state_device": (i32, [vp, C.POINTER(vp)]),

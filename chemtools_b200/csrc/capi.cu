@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -60,16 +61,36 @@ struct DevBuf {
 
 MechDesc make_desc(const CompiledMech& C) {
   MechDesc d{};
-  d.K = C.K; d.R = C.R; d.nf = C.n_fall; d.n3 = C.n_3b; d.KP = C.KP; d.nc = C.n_const; d.Rgas = C.gas_constant; d.p_ref = C.p_ref; d.kc_Tmin = C.kc_fast_Tmin;
+  d.K = C.K; d.R = C.R; d.nf = C.n_fall; d.n3 = C.n_3b; d.KP = C.KP; d.nc = C.n_const; d.nx = C.n_exp_end; d.Rgas = C.gas_constant; d.p_ref = C.p_ref; d.kc_Tmin = C.kc_fast_Tmin;
   const auto& o = C.off;
   d.o_W = o.W; d.o_rW = o.rW; d.o_Tmid = o.Tmid; d.o_nasa = o.nasa; d.o_A = o.A; d.o_b = o.b; d.o_E = o.E; d.o_A0 = o.A0;
   d.o_b0 = o.b0; d.o_E0 = o.E0; d.o_ta = o.troe_a; d.o_rt3 = o.troe_rt3; d.o_rt1 = o.troe_rt1; d.o_t2 = o.troe_t2;
   d.o_eff_val = o.eff_val; d.o_eff_ptr = o.eff_ptr; d.o_sp_ptr = o.sp_ptr; d.o_sp_rxn = o.sp_rxn; d.o_sp_nu = o.sp_nu;
-  d.o_eff_sp = o.eff_sp; d.o_ftype = o.ftype; d.o_stoich = o.stoich; d.o_ent = o.ent; d.o_pstart = o.pstart; d.o_pnplus = o.pnplus;
+  d.o_eff_o = o.eff_o; d.o_ftype = o.ftype; d.o_rxo = o.rxo; d.o_ent = o.ent; d.o_pstart = o.pstart; d.o_pnplus = o.pnplus;
   d.o_lpp = o.lpp; d.o_spp = o.spp; d.n_pieces = o.n_pieces;
   d.blob_bytes = o.total;
   static_assert(sizeof(MechDesc) <= CT_GANG_OFF && CT_POOL_OFF + 16 <= CT_HDR_BYTES, "MechDesc must fit the shared header");
+  static_assert(offsetof(MechDesc, Rgas) == 4 * CT_DESC_INTS_A && offsetof(MechDesc, o_W) == 4 * CT_DESC_INTS_A + 24 &&
+                offsetof(MechDesc, blob_bytes) == 4 * CT_DESC_INTS_A + 24 + 4 * (CT_DESC_INTS_B - 1), "MechDesc word layout (CT_STATIC_SHAPE)");
   return d;
+}
+
+// which compile-time shape (kernels.cuh: CT_STATIC_SHAPE, mech_shapes.inc) a mechanism matches word for word: 1 GRI-3.0,
+// 2 GRI-2.11, 3 GRI-1.2, 0 none (run-time shape)
+template <class SH>
+bool shape_matches(const MechDesc& d) {
+  const int* w = SH::words();
+  const int* a = reinterpret_cast<const int*>(&d);
+  const int* b = reinterpret_cast<const int*>(&d.o_W);
+  for (int i = 0; i < CT_DESC_INTS_A; ++i) if (a[i] != w[i]) return false;
+  for (int i = 0; i < CT_DESC_INTS_B; ++i) if (b[i] != w[CT_DESC_INTS_A + i]) return false;
+  return true;
+}
+int static_shape_of(const MechDesc& d) {
+  if (shape_matches<ShapeGri30>(d)) return 1;
+  if (shape_matches<ShapeGri211>(d)) return 2;
+  if (shape_matches<ShapeGri12>(d)) return 3;
+  return 0;
 }
 
 struct DeviceInfo { int sms = 0; int max_smem_optin = 0; };
@@ -87,6 +108,7 @@ struct ct_mech {
   MechanismDef def;
   CompiledMech C;
   MechDesc desc{};
+  int shape = 0;  // static_shape_of(desc)
   std::map<int, std::pair<unsigned char*, int*>> dev;  // device ordinal -> (blob, perm)
   ~ct_mech() {
     for (auto& kv : dev) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
@@ -121,11 +143,12 @@ struct ct_batch {
   int max_order = 5, jac_mode = CT_JAC_ANALYTIC, ign_mode = 1, linsol = LINSOL_INVERSE;
   double ign_value = 400.0, jac_clip = 10.0;
   int gang = 1, pool_enabled = 1, pool_n = 0, pool_warps = 12, gang_groups = 1, gang_sleep_ns = 200, gang_max_polls = 0, gang_period = 1;
-  bool have_ic = false, fresh = true, roberts = false;
+  bool have_ic = false, fresh = true, roberts = false, use_static_shape = true, atol_is_vec = false;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuf<double> T0, p0, Y0, rho0, state, save, traj, tau, tcur, scratch, tab_t, tab_T, tab_p, atol_vec, tmp_in, tmp_out, tmp_w, tmp_qf, tmp_qr, tmp_t;
   DevBuf<long long> stats;
+  DevBuf<double> stats_ex;  // qlast, qcur, hinused, hlast, hcur, tcur per reactor
   DevBuf<int> status, order;
   DevBuf<unsigned long long> counter;
   DevBuf<long long> timeline; int timeline_on = 0;
@@ -192,10 +215,10 @@ BatchArgs make_args(ct_batch* b) {
   a.n_out = 0; a.n = b->n; a.mxstep = b->mxstep; a.linsol = b->linsol; a.jac_clip = b->jac_clip; a.gang = b->gang; a.pool_n = b->pool_n; a.gang_groups = b->gang_groups; a.gang_sleep_ns = b->gang_sleep_ns; a.gang_max_polls = b->gang_max_polls; a.gang_period = b->gang_period;
   a.T0 = b->pT0; a.p0 = b->pp0; a.rho0 = b->rho0.p;
   a.nt = b->nt; a.tab_t = b->tab_t.p; a.tab_T = b->tab_T.p; a.tab_p = b->tab_p.p;
-  a.rtol = b->rtol; a.atol = b->atol; a.atol_vec = b->atol_vec.n ? b->atol_vec.p : nullptr;
+  a.rtol = b->rtol; a.atol = b->atol; a.atol_vec = (b->atol_is_vec || b->roberts) && b->atol_vec.n ? b->atol_vec.p : nullptr;
   a.t_target = b->t_stop; a.t_stop = b->t_stop; a.ign_value = b->ign_value;
   a.state = b->state.p; a.save = nullptr; a.save_stride = CT_SAVE_DOUBLES; a.traj = nullptr;
-  a.tau = b->tau.p; a.tcur = b->tcur.p; a.stats = b->stats.p; a.status = b->status.p; a.counter = b->counter.p;
+  a.tau = b->tau.p; a.tcur = b->tcur.p; a.stats = b->stats.p; a.stats_ex = b->stats_ex.p; a.status = b->status.p; a.counter = b->counter.p;
   a.scratch = b->scratch.p; a.order = b->have_order ? b->order.p : nullptr;
   a.timeline = b->timeline_on ? b->timeline.p : nullptr;
   a.opts = b->opts; a.t_start = b->t_start;
@@ -223,7 +246,7 @@ int ensure_runtime_buffers(ct_batch* b) {
     CT_CUDA(b->ring.alloc(b->ring_cap)); CT_CUDA(b->ring_seq.alloc(b->ring_cap)); CT_CUDA(b->qctl.alloc(4)); CT_CUDA(b->yielded.alloc(b->n));
     CT_CUDA(b->save.alloc((size_t)b->n * (CT_SAVE_DOUBLES)));
   }
-  CT_CUDA(b->tau.alloc(b->n)); CT_CUDA(b->tcur.alloc(b->n)); CT_CUDA(b->stats.alloc((size_t)b->n * 8));
+  CT_CUDA(b->tau.alloc(b->n)); CT_CUDA(b->tcur.alloc(b->n)); CT_CUDA(b->stats.alloc((size_t)b->n * 8)); CT_CUDA(b->stats_ex.alloc((size_t)b->n * 6));
   CT_CUDA(b->status.alloc(b->n)); CT_CUDA(b->counter.alloc(1));
   if (!b->ev0) { CT_CUDA(cudaEventCreate(&b->ev0)); CT_CUDA(cudaEventCreate(&b->ev1)); }
   return 0;
@@ -240,16 +263,22 @@ int launch_integrate(ct_batch* b, BatchArgs& a) {
     b->aux_launches += 1;
   }
   CT_CUDA(cudaEventRecord(b->ev0, b->stream));
-  if (b->wpb <= 8) {
-    if (int r = set_smem(k_integrate<256>, b->smem)) return r;
-    k_integrate<256><<<b->grid, b->wpb * 32, b->smem, b->stream>>>(d, blob, a);
-  } else if (b->wpb <= 12) {
-    if (int r = set_smem(k_integrate<384>, b->smem)) return r;
-    k_integrate<384><<<b->grid, b->wpb * 32, b->smem, b->stream>>>(d, blob, a);
-  } else {
-    if (int r = set_smem(k_integrate<512>, b->smem)) return r;
-    k_integrate<512><<<b->grid, b->wpb * 32, b->smem, b->stream>>>(d, blob, a);
-  }
+  // specialised kernels (compile-time mechanism shape) for the 12-warp pool configuration of the GRI mechanisms, the
+  // run-time shape otherwise
+  const int shape = (b->mech && b->use_static_shape) ? b->mech->shape : 0;
+#define CT_LAUNCH(MAXT, SH)                                                            \
+  do {                                                                                 \
+    if (int r = set_smem(k_integrate<MAXT, SH>, b->smem)) return r;                    \
+    k_integrate<MAXT, SH><<<b->grid, b->wpb * 32, b->smem, b->stream>>>(d, blob, a);   \
+  } while (0)
+  if (b->wpb <= 8) CT_LAUNCH(256, ShapeRt);
+  else if (b->wpb <= 12) {
+    if (shape == 1) CT_LAUNCH(384, ShapeGri30);
+    else if (shape == 2) CT_LAUNCH(384, ShapeGri211);
+    else if (shape == 3) CT_LAUNCH(384, ShapeGri12);
+    else CT_LAUNCH(384, ShapeRt);
+  } else CT_LAUNCH(512, ShapeRt);
+#undef CT_LAUNCH
   CT_CUDA(cudaGetLastError());
   CT_CUDA(cudaEventRecord(b->ev1, b->stream));
   CT_CUDA(cudaStreamSynchronize(b->stream));
@@ -398,6 +427,7 @@ ct_mech* ct_mech_load_ex(const char* path, const char* phase_id, const char* con
     m->def = is_ctm ? read_ctm(p) : parse_cti(p, phase_id);
     m->C = compile_mechanism(m->def, constants ? constants : "");
     m->desc = make_desc(m->C);
+    m->shape = static_shape_of(m->desc);
     if (m->C.K + 1 > CT_NP) { set(fail(CT_ERR_UNSUPPORTED, "more than 63 species: the warp-per-reactor kernels hold 2 state components per lane")); return nullptr; }
     if (m->C.n_fall + m->C.n_3b > CT_NP) { set(fail(CT_ERR_UNSUPPORTED, "more than 64 third-body/falloff reactions")); return nullptr; }
     set(0);
@@ -512,7 +542,24 @@ int ct_batch_set_tolerances(ct_batch* b, double rtol, double atol) {
   if (!b) return fail(CT_ERR_INVALID, "null batch");
   // same validation as IStrategy::Initialise (interface.cpp:300-317): negative tolerances are illegal
   if (!(rtol >= 0.0) || !(atol >= 0.0) || (rtol == 0.0 && atol == 0.0)) return fail(CT_ILL_INPUT, "tolerances must be non-negative and not both zero");
-  b->rtol = rtol; b->atol = atol;
+  b->rtol = rtol; b->atol = atol; b->atol_is_vec = false;
+  return 0;
+}
+// Client::SetTolerances(rtol, vector atol) (client.hpp:122-134, types.hpp:114-138) -> CVodeSVtolerances: one absolute
+// tolerance per state component (N entries: [T, Y_0..] or [Y_0..]), shared by all reactors of the batch
+int ct_batch_set_tolerances_vec(ct_batch* b, double rtol, const double* atol) {
+  if (!b || !atol) return fail(CT_ERR_INVALID, "null argument");
+  if (!(rtol >= 0.0)) return fail(CT_ILL_INPUT, "relative tolerance must be non-negative");
+  bool any = rtol > 0.0;
+  for (int i = 0; i < b->N; ++i) {
+    if (!(atol[i] >= 0.0)) return fail(CT_ILL_INPUT, "absolute tolerances must be non-negative");
+    any = any || atol[i] > 0.0;
+  }
+  if (!any) return fail(CT_ILL_INPUT, "tolerances must not all be zero");
+  CT_CUDA(b->atol_vec.alloc(b->N));
+  CT_CUDA(cudaMemcpyAsync(b->atol_vec.p, atol, b->N * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+  CT_CUDA(cudaStreamSynchronize(b->stream));
+  b->rtol = rtol; b->atol = 0.0; b->atol_is_vec = true;
   return 0;
 }
 int ct_batch_set_stop_time(ct_batch* b, double t_end) {
@@ -521,7 +568,13 @@ int ct_batch_set_stop_time(ct_batch* b, double t_end) {
   b->t_stop = t_end;
   return 0;
 }
-int ct_batch_set_max_steps(ct_batch* b, int64_t mx) { if (!b) return fail(CT_ERR_INVALID, "null batch"); b->mxstep = mx > 0 ? mx : 500; return 0; }
+// IStrategy::SetMaxNumSteps (interface.cpp:100-106): negative values are refused; 0 selects CVODE's default of 500
+int ct_batch_set_max_steps(ct_batch* b, int64_t mx) {
+  if (!b) return fail(CT_ERR_INVALID, "null batch");
+  if (mx < 0) return fail(CT_ILL_INPUT, "SetMaxNumSteps: maximum number of steps must be non-negative");
+  b->mxstep = mx > 0 ? mx : 500;
+  return 0;
+}
 int ct_batch_set_max_order(ct_batch* b, int q) {
   if (!b) return fail(CT_ERR_INVALID, "null batch");
   if (q < 1 || q > 5) return fail(CT_ILL_INPUT, "BDF order must be in 1..5");
@@ -607,15 +660,26 @@ int ct_batch_set_jacobian(ct_batch* b, int mode) {
 }
 int ct_batch_set_linear_solver(ct_batch* b, int mode) {
   if (!b || (mode != LINSOL_LU && mode != LINSOL_INVERSE)) return fail(CT_ERR_INVALID, "bad linear solver mode");
+  if (!b->fresh) return fail(CT_ILL_INPUT, "the linear solver can only change on a fresh batch (set the initial conditions again)");
   b->linsol = mode;
   return 0;
 }
+// the scratch / save-area indexing of a batch that has been integrated part of the way (Integrate(t < t_stop)) depends on
+// these options: they may only change on a fresh batch (after set_ic / reinit)
+#define CT_REQUIRE_FRESH(b) do { if (!(b)->fresh) return fail(CT_ILL_INPUT, "scheduling layout options can only change on a fresh batch (set the initial conditions again)"); } while (0)
 int ct_batch_set_matrix_pool(ct_batch* b, int on, int warps_per_sm) {
   if (!b) return fail(CT_ERR_INVALID, "null batch");
+  CT_REQUIRE_FRESH(b);
   b->pool_enabled = on ? 1 : 0;
   if (warps_per_sm > 0) b->pool_warps = warps_per_sm;
   return 0;
 }
+int ct_batch_set_static_shape(ct_batch* b, int on) {
+  if (!b) return fail(CT_ERR_INVALID, "null batch");
+  b->use_static_shape = on != 0;
+  return 0;
+}
+int ct_mech_static_shape(const ct_mech* m) { return m ? m->shape : fail(CT_ERR_INVALID, "null mech"); }
 int ct_batch_set_phase_alignment(ct_batch* b, int on) {
   if (!b) return fail(CT_ERR_INVALID, "null batch");
   b->gang = on ? 1 : 0;
@@ -640,6 +704,7 @@ int ct_batch_set_alignment_max_polls(ct_batch* b, int polls) {
 }
 int ct_batch_set_time_slicing(ct_batch* b, int steps) {
   if (!b || steps < 0) return fail(CT_ERR_INVALID, "bad argument");
+  CT_REQUIRE_FRESH(b);
   b->slice_steps = steps;
   return 0;
 }
@@ -699,8 +764,19 @@ int ct_batch_set_tp_table(ct_batch* b, int nt, const double* t, const double* T,
 int ct_batch_set_order(ct_batch* b, const int32_t* order) {
   if (!b) return fail(CT_ERR_INVALID, "null batch");
   if (!order) { b->have_order = false; return 0; }
+  // must be a permutation of 0..n-1: an out-of-range entry would index past the state arrays, a duplicate would make
+  // two warps integrate the same reactor
+  {
+    std::vector<bool> seen((size_t)b->n, false);
+    for (int64_t i = 0; i < b->n; ++i) {
+      const int32_t o = order[i];
+      if (o < 0 || (int64_t)o >= b->n || seen[(size_t)o]) return fail(CT_ERR_INVALID, "order must be a permutation of 0..n-1");
+      seen[(size_t)o] = true;
+    }
+  }
   CT_CUDA(b->order.alloc(b->n));
   CT_CUDA(cudaMemcpyAsync(b->order.p, order, b->n * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+  CT_CUDA(cudaStreamSynchronize(b->stream));  // the caller's array may go away
   b->have_order = true;
   return 0;
 }
@@ -715,7 +791,6 @@ static int precheck_integrate(ct_batch* b) {
 int ct_batch_integrate(ct_batch* b, double t_target) {
   if (int r = precheck_integrate(b)) return r;
   if (b->n == 0) return CT_SUCCESS;
-  if (!(t_target > 0.0)) return fail(CT_ILL_INPUT, "t_target must be positive");
   if (b->fresh && !(t_target > b->t_start)) return fail(CT_ILL_INPUT, "t_target must follow the start time");
   BatchArgs a = make_args(b);
   a.t_target = t_target;
@@ -732,6 +807,87 @@ int ct_batch_integrate(ct_batch* b, double t_target) {
   b->fresh = false;
   int out = 0;
   if (int r = summarize_status(b, &out)) return r;
+  return out;
+}
+
+// Integrate to the stop time, then re-run the reactors that ended with a negative CVODE status as a small batch under
+// other Jacobian / Newton options and merge what succeeded (the recovery IStrategy::Integrate only sketches,
+// interface.cpp:462-473).  About 0.05 % of stiff CH4 ensembles crawl into CV_TOO_MUCH_WORK / CV_ERR_FAILURE: a property of
+// the clipped right-hand side shared with the reference's algorithm, chaotic in which reactor it hits, so a
+// second attempt under different arithmetic almost always gets through.  Ladder: Jacobian clip 1, then LU instead of
+// the inverse, then difference-quotient Jacobian + LU (the reference's own configuration).
+int ct_batch_integrate_with_retry(ct_batch* b, int64_t* n_failed_first, int64_t* n_failed_final) {
+  if (!b) return fail(CT_ERR_INVALID, "null batch");
+  if (!b->fresh) return fail(CT_ILL_INPUT, "IntegrateWithRetry needs a fresh batch (set the initial conditions again)");
+  int rc = ct_batch_integrate(b, b->t_stop);
+  if (rc <= CT_ERR_INVALID) return rc;
+  std::vector<int> st(b->n);
+  CT_CUDA(cudaMemcpy(st.data(), b->status.p, b->n * sizeof(int), cudaMemcpyDeviceToHost));
+  std::vector<int> bad;
+  for (int64_t i = 0; i < b->n; ++i) if (st[i] < 0) bad.push_back((int)i);
+  if (n_failed_first) *n_failed_first = (int64_t)bad.size();
+  struct Alt { double clip; int linsol, jac; };
+  const Alt ladder[3] = {{1.0, LINSOL_INVERSE, CT_JAC_ANALYTIC}, {b->jac_clip, LINSOL_LU, CT_JAC_ANALYTIC}, {b->jac_clip, LINSOL_LU, CT_JAC_DQ}};
+  const int K = b->K, N = b->N;
+  for (int step = 0; step < 3 && !bad.empty(); ++step) {
+    const int m = (int)bad.size();
+    int stc = 0;
+    ct_batch* r = ct_batch_create(b->mech, b->rt, m, &stc);
+    if (!r) return stc;
+    std::unique_ptr<ct_batch> guard(r);
+    r->stream = b->stream; r->rtol = b->rtol; r->atol = b->atol; r->t_stop = b->t_stop; r->mxstep = b->mxstep; r->opts = b->opts;
+    r->max_order = b->max_order; r->ign_mode = b->ign_mode; r->ign_value = b->ign_value; r->use_static_shape = b->use_static_shape;
+    r->jac_clip = ladder[step].clip; r->linsol = ladder[step].linsol; r->jac_mode = ladder[step].jac;
+    if (b->atol_is_vec) {
+      CT_CUDA(r->atol_vec.alloc(N));
+      CT_CUDA(cudaMemcpyAsync(r->atol_vec.p, b->atol_vec.p, N * sizeof(double), cudaMemcpyDeviceToDevice, b->stream));
+      r->atol_is_vec = true;
+    }
+    DevBuf<int> idx, ok;
+    CT_CUDA(idx.alloc(m)); CT_CUDA(ok.alloc(m));
+    CT_CUDA(cudaMemcpyAsync(idx.p, bad.data(), m * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+    CT_CUDA(r->T0.alloc(m)); CT_CUDA(r->p0.alloc(m)); CT_CUDA(r->Y0.alloc((size_t)m * K));
+    const int thr = 256;
+    auto blocks = [&](int64_t work) { return (int)std::max<int64_t>(1, std::min<int64_t>((work + thr - 1) / thr, 2048)); };
+    k_gather_rows<double><<<blocks(m), thr, 0, b->stream>>>(b->pT0, idx.p, m, 1, r->T0.p);
+    k_gather_rows<double><<<blocks(m), thr, 0, b->stream>>>(b->pp0, idx.p, m, 1, r->p0.p);
+    k_gather_rows<double><<<blocks((int64_t)m * K), thr, 0, b->stream>>>(b->pY0, idx.p, m, K, r->Y0.p);
+    CT_CUDA(cudaGetLastError());
+    r->pT0 = r->T0.p; r->pp0 = r->p0.p; r->pY0 = r->Y0.p;
+    if (int e = finish_ic(r)) return e;
+    if (b->rt == CT_TABLE_TP) {
+      CT_CUDA(r->tab_t.alloc(b->nt)); CT_CUDA(r->tab_T.alloc((size_t)m * b->nt)); CT_CUDA(r->tab_p.alloc((size_t)m * b->nt));
+      CT_CUDA(cudaMemcpyAsync(r->tab_t.p, b->tab_t.p, b->nt * sizeof(double), cudaMemcpyDeviceToDevice, b->stream));
+      k_gather_rows<double><<<blocks((int64_t)m * b->nt), thr, 0, b->stream>>>(b->tab_T.p, idx.p, m, b->nt, r->tab_T.p);
+      k_gather_rows<double><<<blocks((int64_t)m * b->nt), thr, 0, b->stream>>>(b->tab_p.p, idx.p, m, b->nt, r->tab_p.p);
+      CT_CUDA(cudaGetLastError());
+      r->nt = b->nt;
+    }
+    if (b->t_start != 0.0) {  // ReInitialise'd batch: restart the retried reactors from the same state and time
+      return fail(CT_ERR_UNSUPPORTED, "IntegrateWithRetry after ReInitialise is not supported");
+    }
+    const int rr = ct_batch_integrate(r, b->t_stop);
+    if (rr <= CT_ERR_INVALID) return rr;
+    b->launches += r->launches; b->aux_launches += r->aux_launches + 3;
+    // merge the reactors that got through (ok[r] = their new status >= 0)
+    CT_CUDA(cudaMemcpyAsync(ok.p, r->status.p, m * sizeof(int), cudaMemcpyDeviceToDevice, b->stream));
+    k_scatter_rows<double><<<blocks((int64_t)m * N), thr, 0, b->stream>>>(r->state.p, idx.p, ok.p, m, N, b->state.p);
+    k_scatter_rows<double><<<blocks(m), thr, 0, b->stream>>>(r->tau.p, idx.p, ok.p, m, 1, b->tau.p);
+    k_scatter_rows<double><<<blocks(m), thr, 0, b->stream>>>(r->tcur.p, idx.p, ok.p, m, 1, b->tcur.p);
+    k_scatter_rows<long long><<<blocks((int64_t)m * 8), thr, 0, b->stream>>>(r->stats.p, idx.p, ok.p, m, 8, b->stats.p);
+    k_scatter_rows<double><<<blocks((int64_t)m * 6), thr, 0, b->stream>>>(r->stats_ex.p, idx.p, ok.p, m, 6, b->stats_ex.p);
+    k_scatter_rows<int><<<blocks(m), thr, 0, b->stream>>>(r->status.p, idx.p, ok.p, m, 1, b->status.p);
+    CT_CUDA(cudaGetLastError());
+    std::vector<int> rs(m);
+    CT_CUDA(cudaMemcpyAsync(rs.data(), r->status.p, m * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CT_CUDA(cudaStreamSynchronize(b->stream));
+    std::vector<int> still;
+    for (int j = 0; j < m; ++j) if (rs[j] < 0) still.push_back(bad[j]);
+    bad.swap(still);
+  }
+  if (n_failed_final) *n_failed_final = (int64_t)bad.size();
+  int out = 0;
+  if (int e = summarize_status(b, &out)) return e;
   return out;
 }
 
@@ -779,6 +935,13 @@ int ct_batch_get_stats(ct_batch* b, int64_t* out) {
   if (!b || !out) return fail(CT_ERR_INVALID, "null argument");
   if (!b->stats.p || b->launches == 0) return fail(CT_ILL_INPUT, "nothing integrated yet");
   CT_CUDA(cudaMemcpyAsync(out, b->stats.p, (size_t)b->n * 8 * sizeof(long long), cudaMemcpyDeviceToHost, b->stream));
+  CT_CUDA(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+int ct_batch_get_stats_ex(ct_batch* b, double* out) {
+  if (!b || !out) return fail(CT_ERR_INVALID, "null argument");
+  if (!b->stats_ex.p || b->launches == 0) return fail(CT_ILL_INPUT, "nothing integrated yet");
+  CT_CUDA(cudaMemcpyAsync(out, b->stats_ex.p, (size_t)b->n * 6 * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
   CT_CUDA(cudaStreamSynchronize(b->stream));
   return 0;
 }
@@ -881,18 +1044,27 @@ int ct_rhs_time_cfg(ct_batch* b, const double* states, int reps, int warps_per_b
   BatchArgs a = make_args(b);
   a.pool_n = 1;  // slab without the matrix
   const int threads = warps_per_block * 32, grid = di.sms * blocks_per_sm;
+  const bool st30 = b->use_static_shape && b->mech->shape == 1;
+#define CT_RHS_ARGS b->mech->desc, blob, a, b->tmp_in.p, nullptr, b->tmp_out.p, b->tmp_w.p, nullptr, nullptr, perm
   auto launch = [&]() {
-    if (threads <= 256) k_rhs_t<256><<<grid, threads, smem, b->stream>>>(b->mech->desc, blob, a, b->tmp_in.p, nullptr, b->tmp_out.p, b->tmp_w.p, nullptr, nullptr, perm);
-    else if (threads <= 384) k_rhs_t<384><<<grid, threads, smem, b->stream>>>(b->mech->desc, blob, a, b->tmp_in.p, nullptr, b->tmp_out.p, b->tmp_w.p, nullptr, nullptr, perm);
-    else if (threads <= 512) k_rhs_t<512><<<grid, threads, smem, b->stream>>>(b->mech->desc, blob, a, b->tmp_in.p, nullptr, b->tmp_out.p, b->tmp_w.p, nullptr, nullptr, perm);
-    else if (threads <= 768) k_rhs_t<768><<<grid, threads, smem, b->stream>>>(b->mech->desc, blob, a, b->tmp_in.p, nullptr, b->tmp_out.p, b->tmp_w.p, nullptr, nullptr, perm);
-    else k_rhs_t<1024><<<grid, threads, smem, b->stream>>>(b->mech->desc, blob, a, b->tmp_in.p, nullptr, b->tmp_out.p, b->tmp_w.p, nullptr, nullptr, perm);
+    if (st30) {
+      if (threads <= 384) k_rhs_t<384, ShapeGri30><<<grid, threads, smem, b->stream>>>(CT_RHS_ARGS);
+      else if (threads <= 512) k_rhs_t<512, ShapeGri30><<<grid, threads, smem, b->stream>>>(CT_RHS_ARGS);
+      else k_rhs_t<768, ShapeGri30><<<grid, threads, smem, b->stream>>>(CT_RHS_ARGS);
+    } else {
+      if (threads <= 384) k_rhs_t<384, ShapeRt><<<grid, threads, smem, b->stream>>>(CT_RHS_ARGS);
+      else if (threads <= 512) k_rhs_t<512, ShapeRt><<<grid, threads, smem, b->stream>>>(CT_RHS_ARGS);
+      else k_rhs_t<768, ShapeRt><<<grid, threads, smem, b->stream>>>(CT_RHS_ARGS);
+    }
   };
-  if (int r = set_smem(k_rhs_t<256>, smem)) return r;
-  if (int r = set_smem(k_rhs_t<384>, smem)) return r;
-  if (int r = set_smem(k_rhs_t<512>, smem)) return r;
-  if (int r = set_smem(k_rhs_t<768>, smem)) return r;
-  if (int r = set_smem(k_rhs_t<1024>, smem)) return r;
+#undef CT_RHS_ARGS
+  if (threads > 768) return fail(CT_ERR_INVALID, "at most 24 warps per block");
+  if (int r = set_smem(k_rhs_t<384, ShapeGri30>, smem)) return r;
+  if (int r = set_smem(k_rhs_t<512, ShapeGri30>, smem)) return r;
+  if (int r = set_smem(k_rhs_t<768, ShapeGri30>, smem)) return r;
+  if (int r = set_smem(k_rhs_t<384, ShapeRt>, smem)) return r;
+  if (int r = set_smem(k_rhs_t<512, ShapeRt>, smem)) return r;
+  if (int r = set_smem(k_rhs_t<768, ShapeRt>, smem)) return r;
   for (int w = 0; w < 3; ++w) launch();
   CT_CUDA(cudaGetLastError());
   CT_CUDA(cudaEventRecord(b->ev0, b->stream));

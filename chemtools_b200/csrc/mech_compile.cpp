@@ -74,15 +74,23 @@ CompiledMech compile_mechanism(const MechanismDef& D, const std::string& constan
     }
   }
   // device order: falloff | three-body | elementary with a temperature-dependent k_f | elementary with b = 0 and
-  // Ea = 0 (k_f = A: Cantera's A exp(0) is exactly A, so whole lane-passes over that tail skip the exponential);
-  // stable within each class
-  for (int pass = 0; pass < 4; ++pass)
+  // Ea = 0 (k_f = A: Cantera's A exp(0) is exactly A, so the lane-passes over that tail skip the exponential);
+  // stable within each class.  The temperature-dependent region is padded with constant reactions (evaluated as
+  // A exp(0), exact) to a multiple of 32, so the constant tail starts on a lane-pass boundary: n_exp_end.
+  {
+    std::vector<int> cls_list[4];
     for (int i = 0; i < R; ++i) {
       const ReactionDef& r = D.reactions[i];
       const bool constant = r.kind == RxnKind::Elementary && r.kf[1] == 0.0 && r.kf[2] == 0.0;
-      const int cls = r.kind == RxnKind::Falloff ? 0 : r.kind == RxnKind::ThreeBody ? 1 : constant ? 3 : 2;
-      if (cls == pass) { C.perm.push_back(i); if (constant) C.n_const++; }
+      cls_list[r.kind == RxnKind::Falloff ? 0 : r.kind == RxnKind::ThreeBody ? 1 : constant ? 3 : 2].push_back(i);
     }
+    size_t moved = 0;
+    while (cls_list[2].size() % 32 != 0 && moved < cls_list[3].size()) cls_list[2].push_back(cls_list[3][moved++]);
+    cls_list[3].erase(cls_list[3].begin(), cls_list[3].begin() + moved);
+    for (int c = 0; c < 4; ++c) for (int i : cls_list[c]) C.perm.push_back(i);
+    C.n_const = (int)cls_list[3].size();
+    C.n_exp_end = (int)(cls_list[0].size() + cls_list[1].size() + cls_list[2].size());
+  }
   C.inv_perm.assign(R, 0);
   for (int d = 0; d < R; ++d) C.inv_perm[C.perm[d]] = d;
   // Kinetics::reactionString: Cantera rebuilds the text from its species->coefficient std::map, i.e. species in
@@ -119,7 +127,8 @@ CompiledMech compile_mechanism(const MechanismDef& D, const std::string& constan
   }
   std::vector<double> A(R), b(R), E(R), A0(nf), b0(nf), E0(nf), ta(nf), rt3(nf), rt1(nf), t2(nf), eff_val;
   std::vector<int> eff_ptr(nf + n3 + 1, 0);
-  std::vector<unsigned char> eff_sp, ftype(nf, 0), rev(R), reac((size_t)3 * R, (unsigned char)K), prod((size_t)3 * R, (unsigned char)K);
+  std::vector<unsigned short> eff_o;  // collider species as byte offsets into the per-warp {c, 1/E} pair array (16 * k)
+  std::vector<unsigned char> ftype(nf, 0), rev(R), reac((size_t)3 * R, (unsigned char)K), prod((size_t)3 * R, (unsigned char)K);
   std::vector<signed char> dn(R);
   // species -> reaction lists with net stoichiometric coefficient
   std::vector<std::vector<std::pair<int, int>>> sp_list(K);
@@ -171,10 +180,10 @@ CompiledMech compile_mechanism(const MechanismDef& D, const std::string& constan
       for (auto& e : r.efficiencies) {
         auto it = sp_index.find(e.first);
         if (it == sp_index.end()) throw MechError("undeclared collider '" + e.first + "' in: " + r.equation);
-        eff_sp.push_back((unsigned char)it->second);
+        eff_o.push_back((unsigned short)(16 * it->second));
         eff_val.push_back(e.second - 1.0);
       }
-      eff_ptr[d + 1] = (int)eff_sp.size();
+      eff_ptr[d + 1] = (int)eff_o.size();
     } else if (!r.efficiencies.empty()) {
       throw MechError("efficiencies on an elementary reaction: " + r.equation);
     }
@@ -211,18 +220,19 @@ CompiledMech compile_mechanism(const MechanismDef& D, const std::string& constan
   o.troe_a = append(C.blob, ta); o.troe_rt3 = append(C.blob, rt3); o.troe_rt1 = append(C.blob, rt1); o.troe_t2 = append(C.blob, t2);
   o.eff_val = append(C.blob, eff_val); o.eff_ptr = append(C.blob, eff_ptr); o.sp_ptr = append(C.blob, sp_ptr);
   o.sp_rxn = append(C.blob, sp_rxn); o.sp_nu = append(C.blob, sp_nu);
-  o.eff_sp = append(C.blob, eff_sp); o.ftype = append(C.blob, ftype);
-  // packed stoichiometry: bytes 0-2 reactant slots, 3-5 product slots (K = none), 6 reversible, 7 dn + 2
-  std::vector<unsigned long long> stoich(R);
+  o.eff_o = append(C.blob, eff_o); o.ftype = append(C.blob, ftype);
+  // packed reaction records, 16 bytes each (one LDS.128): six 16-bit byte offsets, pre-scaled for the arrays the
+  // right-hand side indexes with them -- reactant slots 16 * k into the per-warp {c_k, 1/E_k} pair array, product slots
+  // 8 * k into the c_k E_k array (K = "no species": a slot that holds 1.0) -- then 8 * index into the per-warp table of
+  // C^-dn factors {C^2, C, 1, 1/C, 1/C^2, 0} (index dn + 2; 5 = irreversible: no reverse rate), then a spare.
+  std::vector<unsigned short> rxo((size_t)8 * R, 0);
   for (int d = 0; d < R; ++d) {
-    unsigned long long w = 0;
-    for (int sl = 0; sl < 3; ++sl) w |= (unsigned long long)reac[(size_t)sl * R + d] << (8 * sl);
-    for (int sl = 0; sl < 3; ++sl) w |= (unsigned long long)prod[(size_t)sl * R + d] << (8 * (3 + sl));
-    w |= (unsigned long long)rev[d] << 48;
-    w |= (unsigned long long)(unsigned char)(dn[d] + 2) << 56;
-    stoich[d] = w;
+    for (int sl = 0; sl < 3; ++sl) rxo[(size_t)8 * d + sl] = (unsigned short)(16 * reac[(size_t)sl * R + d]);
+    for (int sl = 0; sl < 3; ++sl) rxo[(size_t)8 * d + 3 + sl] = (unsigned short)(8 * prod[(size_t)sl * R + d]);
+    if (dn[d] < -2 || dn[d] > 2) throw MechError("change of mole number outside -2..2 in: " + D.reactions[C.perm[d]].equation);
+    rxo[(size_t)8 * d + 6] = (unsigned short)(8 * (rev[d] ? dn[d] + 2 : 5));
   }
-  o.stoich = append(C.blob, stoich);
+  o.rxo = append(C.blob, rxo);
   // balanced gather tables for wdot: the species-sorted entry list (|nu| = 2 entries duplicated) is cut at species
   // boundaries and at multiples of ceil(nnz/32); lane l owns the pieces that start inside its chunk.
   {
@@ -271,7 +281,7 @@ CompiledMech compile_mechanism(const MechanismDef& D, const std::string& constan
     o.lpp = append(C.blob, lpp); o.spp = append(C.blob, spp); o.n_pieces = P;
   }
   while (C.blob.size() % 16) C.blob.push_back(0);
-  o.n_eff = (int)eff_sp.size(); o.n_nnz = (int)sp_rxn.size(); o.total = (int)C.blob.size();
+  o.n_eff = (int)eff_o.size(); o.n_nnz = (int)sp_rxn.size(); o.total = (int)C.blob.size();
 
   // ---- algorithmic flop model (FMA = 2, each fp64 exp/log/log10/pow = 20) ----
   int n_rev = 0, n_troe = 0, n_stoich = 0;
@@ -288,7 +298,7 @@ CompiledMech compile_mechanism(const MechanismDef& D, const std::string& constan
                  + 6.0 * K          /* energy sums, dY/dt */
                  + 5.0 * n_arr      /* Arrhenius argument + scale */
                  + 10.0 * n_rev     /* delta g gather + Kc argument */
-                 + 2.0 * (double)eff_sp.size() + 2.0 * (nf + n3) + 24.0 * nf /* third body, falloff algebra */
+                 + 2.0 * (double)eff_o.size() + 2.0 * (nf + n3) + 24.0 * nf /* third body, falloff algebra */
                  + 6.0 * R          /* concentration products, net */
                  + 2.0 * n_stoich;  /* wdot scatter */
   C.flops_rhs = arith + 20.0 * C.n_transcendental;

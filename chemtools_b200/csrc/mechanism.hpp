@@ -72,6 +72,7 @@ struct CompiledMech {
   int K = 0, R = 0, n_fall = 0, n_3b = 0, KP = 64;
   double kc_fast_Tmin = 400.0;  // above this temperature 1/Kc may be formed from per-species factors exp(mu0/RT) (range check)
   int n_const = 0;  // trailing elementary reactions with b = 0 and Ea = 0 (k_f = A exactly: no exponential needed)
+  int n_exp_end = 0;  // device index where that tail starts (falloff + three-body + temperature-dependent region, the latter padded to a multiple of 32)
   double gas_constant = 0, p_ref = 0;
   std::string constants;
   std::vector<std::string> species_names, equations /*file order*/, elements;
@@ -83,7 +84,7 @@ struct CompiledMech {
   std::vector<unsigned char> blob;
   struct Offsets {
     int W, rW, Tmid, nasa, A, b, E, A0, b0, E0, troe_a, troe_rt3, troe_rt1, troe_t2, eff_val, eff_ptr,
-        sp_ptr, sp_rxn, sp_nu, eff_sp, ftype, stoich, ent, pstart, pnplus, lpp, spp, n_pieces, n_eff, n_nnz, total;
+        sp_ptr, sp_rxn, sp_nu, eff_o, ftype, rxo, ent, pstart, pnplus, lpp, spp, n_pieces, n_eff, n_nnz, total;
   } off{};
   // roofline bookkeeping: algorithmic flop counts per call (SURVEY.md §8d contract)
   double flops_rhs = 0, flops_jac = 0, flops_lu = 0, flops_solve = 0;

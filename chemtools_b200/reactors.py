@@ -22,6 +22,7 @@ CV_SUCCESS, CV_TSTOP_RETURN = 0, 1
 CV_TOO_MUCH_WORK, CV_TOO_MUCH_ACC, CV_ERR_FAILURE, CV_CONV_FAILURE = -1, -2, -3, -4
 
 STAT_NAMES = ("nst", "nfe", "nsetups", "netf", "nni", "ncfn", "nje", "nfeLS")
+STAT_EX_NAMES = ("qlast", "qcur", "hinused", "hlast", "hcur", "tcur")
 
 
 class Type(enum.IntEnum):
@@ -93,6 +94,10 @@ class ThermoKinetics:
 
     def gas_constant(self):
         return lib().ct_mech_gas_constant(self._h)
+
+    def static_shape(self):
+        """1 / 2 / 3 = GRI-3.0 / 2.11 / 1.2 (kernels with compile-time sizes and offsets), 0 = run-time shape."""
+        return lib().ct_mech_static_shape(self._h)
 
     def save_ctm(self, path):
         check(lib().ct_mech_save_ctm(self._h, str(path).encode()))
@@ -172,6 +177,16 @@ class ReactorBatch:
             pass
 
     # ---- options (Solver::Set* of interface.hpp:77-89)
+    def SetTolerances(self, relative, absolute):
+        """Client::SetTolerances (client.hpp:122-134): scalar or per-component (length n_state) absolute tolerance."""
+        if np.ndim(absolute) == 0:
+            check(lib().ct_batch_set_tolerances(self._h, float(relative), float(absolute)))
+        else:
+            a = _f64(absolute)
+            if a.shape != (self.n_state,):
+                raise ValueError("absolute tolerance vector must have n_state entries")
+            check(lib().ct_batch_set_tolerances_vec(self._h, float(relative), _p(a)))
+
     def SetMaxNumSteps(self, n):
         check(lib().ct_batch_set_max_steps(self._h, int(n)))
 
@@ -220,6 +235,9 @@ class ReactorBatch:
 
     def SetJacobianClip(self, thr):
         check(lib().ct_batch_set_jacobian_clip(self._h, float(thr)))
+
+    def SetStaticShape(self, on):
+        check(lib().ct_batch_set_static_shape(self._h, 1 if on else 0))
 
     def SetPhaseAlignment(self, on):
         check(lib().ct_batch_set_phase_alignment(self._h, int(on)))
@@ -306,41 +324,18 @@ class ReactorBatch:
             check(code)
         return code
 
-    def IntegrateWithRetry(self, alternatives=None):
-        """Integrate to the stop time and re-run the reactors that ended with a negative CVODE status (about 0.05 % of
-        stiff CH4 ensembles crawl into CV_TOO_MUCH_WORK: a property of the clipped right-hand side shared with the
-        reference's algorithm, chaotic in which reactor it hits) as a small batch
-        under other Jacobian / Newton options.  Returns dict(state, ignition_delay, statistics, status, retried)."""
-        if self._host_ic is None:
-            raise ValueError("IntegrateWithRetry needs host initial conditions")
-        if alternatives is None:
-            alternatives = ({"jacobian_clip": 1.0}, {"linear_solver": "lu"}, {"jacobian": "dq", "linear_solver": "lu"})
-        self.Integrate(self.t_end)
-        out = dict(state=self.Solution(), ignition_delay=self.IgnitionDelay(), statistics=self.Statistics(), status=self.Status())
-        bad = np.where(out["status"] < 0)[0]
-        out["retried"] = bad
-        T, p, Y = self._host_ic
-        rtol, atol, mxstep = self._ctor
-        for alt in alternatives:
-            if bad.size == 0:
-                break
-            r = ReactorBatch(self.type, self.chem, T[bad], p[bad], Y[bad], rtol, atol, self.t_end, max_num_steps=mxstep)
-            if self._table is not None:
-                r.SetTable(self._table[0], self._table[1][bad], self._table[2][bad])
-            if "jacobian_clip" in alt:
-                r.SetJacobianClip(alt["jacobian_clip"])
-            if "linear_solver" in alt:
-                r.SetLinearSolver(alt["linear_solver"])
-            if "jacobian" in alt:
-                r.SetJacobian(alt["jacobian"])
-            r.Integrate(self.t_end)
-            st = r.Status()
-            ok = st >= 0
-            idx = bad[ok]
-            out["state"][idx] = r.Solution()[ok]; out["ignition_delay"][idx] = r.IgnitionDelay()[ok]
-            out["statistics"][idx] = r.Statistics()[ok]; out["status"][idx] = st[ok]
-            bad = bad[~ok]
-        return out
+    def IntegrateWithRetry(self):
+        """ct_batch_integrate_with_retry: Integrate to the stop time, then the library re-runs the reactors that ended with a
+        negative CVODE status (about 0.05 % of stiff CH4 ensembles crawl into CV_TOO_MUCH_WORK: a property of the clipped
+        right-hand side shared with the reference's algorithm, chaotic in which reactor it hits) as a small
+        batch under other Jacobian / Newton options and merges what succeeded.  Returns dict(code, state, ignition_delay,
+        statistics, status, failed_first, failed_final)."""
+        n0, n1 = C.c_int64(0), C.c_int64(0)
+        code = lib().ct_batch_integrate_with_retry(self._h, C.byref(n0), C.byref(n1))
+        if code <= -100:
+            check(code)
+        return dict(code=code, state=self.Solution(), ignition_delay=self.IgnitionDelay(), statistics=self.Statistics(), status=self.Status(),
+                    failed_first=n0.value, failed_final=n1.value)
 
     def IntegrateTrajectory(self, n_out):
         traj = np.zeros((self.n, n_out, self.n_state))
@@ -383,6 +378,13 @@ class ReactorBatch:
     def Statistics(self):
         out = np.zeros((self.n, 8), dtype=np.int64)
         check(lib().ct_batch_get_stats(self._h, out.ctypes.data_as(lp)))
+        return out
+
+    def StatisticsEx(self):
+        """[n, 6]: last_order_used, current_order, first / last / next internal step size, current time
+        (MainSolverStatistics, include/sundials/cvode/types.hpp:175-215 of the reference)."""
+        out = np.zeros((self.n, 6))
+        check(lib().ct_batch_get_stats_ex(self._h, _p(out)))
         return out
 
     def LastKernelMs(self):

@@ -119,6 +119,9 @@ int ct_batch_set_ic(ct_batch*, const double* T, const double* p, const double* Y
 int ct_batch_set_ic_device(ct_batch*, const double* dT, const double* dp, const double* dY);
 /* Client::SetTolerances (client.hpp:122-134) via Base::SetSolverParameters (base.cpp:112-121) */
 int ct_batch_set_tolerances(ct_batch*, double rtol, double atol);
+/* Client::SetTolerances(rtol, std::vector<realtype> atol) (client.hpp:122-134, types.hpp:114-138) -> CVodeSVtolerances:
+ * one absolute tolerance per state component (N entries), the same for every reactor of the batch */
+int ct_batch_set_tolerances_vec(ct_batch*, double rtol, const double* atol /*N*/);
 /* Client::SetIntegrationTime(0, t_end) (base.cpp:119-120) -> CVodeSetStopTime (interface.cpp:334-343) */
 int ct_batch_set_stop_time(ct_batch*, double t_end);
 /* Solver::SetMaxNumSteps (interface.hpp:80; 500 default, the reactor test uses 20000) */
@@ -157,6 +160,11 @@ int ct_batch_set_linear_solver(ct_batch*, int mode);
 int ct_batch_set_jacobian_clip(ct_batch*, double thr);
 /* scheduling only (results are unaffected): align the warps of a CTA in front of every Newton residual so that they
  * share instruction fetches (the fused kernel is instruction-cache bound); default on */
+/* kernel selection only (results are unaffected): the three shipped GRI mechanisms run kernels whose sizes and blob offsets
+ * are compile-time constants (ct_mech_static_shape: 1 GRI-3.0, 2 GRI-2.11, 3 GRI-1.2, 0 = any other mechanism: run-time
+ * shape); off = run-time shape for every mechanism; default on */
+int ct_batch_set_static_shape(ct_batch*, int on);
+int ct_mech_static_shape(const ct_mech*);
 int ct_batch_set_phase_alignment(ct_batch*, int on); /* 0 off, 1 one group per CTA (default), 2 two groups (even/odd warps) */
 int ct_batch_set_alignment_poll_ns(ct_batch*, int ns); /* sleep between polls of the alignment barrier, default 200 */
 int ct_batch_set_alignment_period(ct_batch*, int period); /* meet at every period-th Newton residual; default 1 */
@@ -191,6 +199,11 @@ int ct_batch_set_order(ct_batch*, const int32_t* order);
  * Returns 0 if every reactor returned CV_SUCCESS, 1 if every live reactor reached the stop time, else the most
  * negative per-reactor code. */
 int ct_batch_integrate(ct_batch*, double t_target);
+/* Integrate(t_stop) followed by a recovery pass over the reactors that ended with a negative CVODE status: they are re-run
+ * as a small batch under other Jacobian / Newton options (Jacobian clip 1, then LU, then difference-quotient Jacobian +
+ * LU) and the successful ones merged; what IStrategy::Integrate only sketches (interface.cpp:462-473).  Fresh batches only.
+ * n_failed_first / n_failed_final (may be NULL): reactors with a negative status before / after the recovery. */
+int ct_batch_integrate_with_retry(ct_batch*, int64_t* n_failed_first, int64_t* n_failed_final);
 /* one launch covering n_out equally spaced outputs t_k = (k+1) t_end / n_out; traj (host) n x n_out x N */
 int ct_batch_integrate_trajectory(ct_batch*, int n_out, double* traj);
 /* Solver::Solution() / Client::State() (client.hpp:110-120): n x N host array */
@@ -202,6 +215,10 @@ int ct_batch_get_status(ct_batch*, int32_t* status /*n*/);
 /* IStrategy::MainSolverStatistics / LinearSolverStatistics (interface.cpp:487-623): per reactor
  * nst, nfe, nsetups, netf, nni, ncfn, nje, nfeLS */
 int ct_batch_get_stats(ct_batch*, int64_t* stats /*n x 8*/);
+/* the rest of MainSolverStatistics (include/sundials/cvode/types.hpp:175-215, filled by CVodeGetLastOrder, GetCurrentOrder,
+ * GetActualInitStep, GetLastStep, GetCurrentStep, GetCurrentTime in interface.cpp:487-560): per reactor
+ * qlast, qcur, hinused, hlast, hcur, tcur (n_stability_order_reductions is always 0: detection is off) */
+int ct_batch_get_stats_ex(ct_batch*, double* stats_ex /*n x 6*/);
 /* device time of the last integrate launch in ms (CUDA events on the launch stream) and launch count so far */
 double ct_batch_last_kernel_ms(const ct_batch*);
 int64_t ct_batch_launch_count(const ct_batch*);

@@ -22,8 +22,13 @@ typedef struct {
   double rtol, atol, t_end; long max_steps; int ign_mode; double ign_value; int n_out;
   double *out_traj, *out_state, *out_tau; long* out_stats; int* out_status;
   const double* opts;
+  double* out_stats_ex; /* optional [n x 6]: qlast, qcur, hinused, hlast, hcur, tcur (MainSolverStatistics of the reference) */
   atomic_long next;
 } batch_job;
+
+/* set by or_set_stats_ex_buffer for the next or_integrate_batch* call of this thread (keeps the call signature) */
+static _Thread_local double* g_stats_ex = NULL;
+void or_set_stats_ex_buffer(double* buf) { g_stats_ex = buf; }
 
 static void run_one(batch_job* J, long i) {
   const omech* m = J->m;
@@ -68,6 +73,10 @@ static void run_one(batch_job* J, long i) {
     long io[10]; double ro[4];
     cvo_stats(c, io, ro);
     for (int s = 0; s < 8; ++s) J->out_stats[i * 8 + s] = io[s];
+    if (J->out_stats_ex) {
+      double* e = J->out_stats_ex + i * 6;
+      e[0] = (double)io[8]; e[1] = (double)io[9]; e[2] = ro[2]; e[3] = ro[0]; e[4] = ro[1]; e[5] = ro[3];
+    }
   }
   if (J->out_status) J->out_status[i] = status;
   cvo_destroy(c);
@@ -101,7 +110,8 @@ int or_integrate_batch_opts(const omech* m, int type, long n, const double* T0, 
                             double* out_state, double* out_tau, long* out_stats, int* out_status,
                             const double* opts) {
   batch_job J = {m, type, n, T0, p0, Y0, nt, tab_t, tab_T, tab_p, rtol, atol, t_end, max_steps,
-                 ign_mode, ign_value, n_out, out_traj, out_state, out_tau, out_stats, out_status, opts, 0};
+                 ign_mode, ign_value, n_out, out_traj, out_state, out_tau, out_stats, out_status, opts, g_stats_ex, 0};
+  g_stats_ex = NULL;
   if (nthreads < 1) nthreads = 1;
   if (nthreads > n) nthreads = (int)(n > 0 ? n : 1);
   if (nthreads == 1) { worker(&J); return 0; }

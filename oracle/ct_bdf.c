@@ -74,6 +74,7 @@ struct cvo {
   int* piv;
   int q, qprime, qwait, L, qmax, qu;
   double h, hprime, eta, hscale, tn, hu, h0u, next_h;
+  int next_q; /* CVodeGetCurrentOrder: order to be attempted on the next step (cv_next_q) */
   double tau[LMAX + 1], tq[6], l[LMAX];
   double rl1, gamma, gammap, gamrat, crate, delp, acnrm;
   int acnrmcur;
@@ -125,7 +126,7 @@ void cvo_init(cvo* c, double t0, const double* y0) {
   memcpy(c->zn[0], y0, c->N * 8);
   c->tn = t0; c->q = 1; c->L = 2; c->qwait = 2; c->etamax = ETAMX1; c->qu = 0; c->hu = 0.0;
   c->nst = c->nfe = c->nsetups = c->netf = c->nni = c->ncfn = c->nje = c->nfeDQ = 0;
-  c->nstlp = c->nstlj = 0; c->h = 0.0; c->h0u = 0.0; c->next_h = 0.0; c->tstopset = 0;
+  c->nstlp = c->nstlj = 0; c->h = 0.0; c->h0u = 0.0; c->next_h = 0.0; c->next_q = 0; c->tstopset = 0;
   c->crate = 1.0; c->saved_tq5 = 0.0; c->gamrat = 1.0; c->gammap = 0.0;
   c->watch_done = 0; c->watch_time = NAN;
   for (int i = 0; i <= LMAX; ++i) c->tau[i] = 0.0;
@@ -155,7 +156,7 @@ void cvo_watch(cvo* c, int comp, double thr) { c->watch_comp = comp; c->watch_th
 double cvo_watch_time(const cvo* c) { return c->watch_time; }
 void cvo_stats(const cvo* c, long* io, double* ro) {
   io[0] = c->nst; io[1] = c->nfe; io[2] = c->nsetups; io[3] = c->netf; io[4] = c->nni;
-  io[5] = c->ncfn; io[6] = c->nje; io[7] = c->nfeDQ; io[8] = c->qu; io[9] = c->q;
+  io[5] = c->ncfn; io[6] = c->nje; io[7] = c->nfeDQ; io[8] = c->qu; io[9] = c->next_q;
   ro[0] = c->hu; ro[1] = c->next_h; ro[2] = c->h0u; ro[3] = c->tn;
 }
 
@@ -618,7 +619,7 @@ int cvo_integrate(cvo* c, double tout, double* yout, double* tret) {
   }
   long nstloc = 0;
   for (;;) {
-    c->next_h = c->h;
+    c->next_h = c->h; c->next_q = c->q;
     if (c->nst > 0 && ewt_set(c, c->zn[0])) { istate = CVO_ILL_INPUT; *tret = c->tn; memcpy(yout, c->zn[0], N * 8); break; }
     if (c->mxstep > 0 && nstloc >= c->mxstep) { istate = CVO_TOO_MUCH_WORK; *tret = c->tn; memcpy(yout, c->zn[0], N * 8); break; }
     double nrm = wrms(N, c->zn[0], c->ewt);
@@ -626,7 +627,7 @@ int cvo_integrate(cvo* c, double tout, double* yout, double* tret) {
     int kflag = cv_step(c);
     if (kflag != 0) { istate = kflag; *tret = c->tn; memcpy(yout, c->zn[0], N * 8); break; }
     nstloc++;
-    if ((c->tn - tout) * c->h >= 0.0) { istate = CVO_SUCCESS; *tret = tout; get_dky0(c, tout, yout); c->next_h = c->hprime; break; }
+    if ((c->tn - tout) * c->h >= 0.0) { istate = CVO_SUCCESS; *tret = tout; get_dky0(c, tout, yout); c->next_h = c->hprime; c->next_q = c->qprime; break; }
     if (c->tstopset) {
       double troundoff = FUZZ_FACTOR * UROUND * (fabs(c->tn) + fabs(c->h));
       if (fabs(c->tn - c->tstop) <= troundoff) { get_dky0(c, c->tstop, yout); *tret = c->tstop; c->tstopset = 0; istate = CVO_TSTOP_RETURN; break; }

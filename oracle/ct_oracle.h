@@ -91,6 +91,8 @@ enum { CVO_SUCCESS = 0, CVO_TSTOP_RETURN = 1, CVO_TOO_MUCH_WORK = -1, CVO_TOO_MU
  * ign_mode 0: threshold = ign_value (absolute K); 1: threshold = T0 + ign_value.
  * out_state n*N, out_tau n, out_stats n*8 (nst,nfe,nsetups,netf,nni,ncfn,nje,nfeDQ), out_status n.
  * If n_out>0, trajectories at t_k=(k+1)*t_end/n_out go to out_traj[n][n_out][N]. */
+/* optional: [n x 6] qlast, qcur, hinused, hlast, hcur, tcur of every reactor, filled by the NEXT or_integrate_batch* call of this thread */
+void or_set_stats_ex_buffer(double* buf);
 int or_integrate_batch(const omech*, int type, long n, const double* T0, const double* p0,
                        const double* Y0, int nt, const double* tab_t, const double* tab_T,
                        const double* tab_p, double rtol, double atol, double t_end, long max_steps,

@@ -82,6 +82,7 @@ def lib():
                                          C.c_int, C.c_int, dp, dp, dp, lp, ip]
         L.or_integrate_batch_opts.argtypes = L.or_integrate_batch.argtypes + [dp]
         L.or_rhs_batch.argtypes = [C.c_void_p, C.c_int, C.c_long, dp, dp, dp, dp, dp, dp, dp, dp]
+        L.or_set_stats_ex_buffer.argtypes = [dp]
         _LIB = L
     return _LIB
 
@@ -265,10 +266,13 @@ class Mechanism:
             # solver option surface of the reference (types.hpp:68-112); 0 = CVODE default
             opts = _f64([options.get(k, 0.0) for k in ("init_step", "min_step", "max_step", "nonlin_conv_coef",
                                                         "max_err_test_fails", "max_nonlin_iters", "max_conv_fails", "max_order")])
+        stats_ex = np.zeros((n, 6))
+        lib().or_set_stats_ex_buffer(_dp(stats_ex))
         lib().or_integrate_batch_opts(self._h, rtype, n, _dp(T0), _dp(p0), _dp(Y0), nt, _dp(tt), _dp(tT), _dp(tp), rtol, atol,
                                       t_end, max_steps, ign_mode, ign_value, nthreads, n_out, _dp(traj), _dp(state), _dp(tau),
                                       stats.ctypes.data_as(C.POINTER(C.c_long)), _ip(status), _dp(opts))
-        return dict(state=state, tau=tau, stats=stats, status=status, traj=traj)
+        # stats_ex columns: qlast, qcur, hinused, hlast, hcur, tcur (include/sundials/cvode/types.hpp:175-215 of the reference)
+        return dict(state=state, tau=tau, stats=stats, status=status, traj=traj, stats_ex=stats_ex)
 
 
 RHS_FN = C.CFUNCTYPE(C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
@@ -318,7 +322,9 @@ class BDF:
     def stats(self):
         io = np.zeros(10, dtype=np.int64); ro = np.zeros(4)
         lib().cvo_stats(self._h, io.ctypes.data_as(C.POINTER(C.c_long)), _dp(ro))
-        return dict(zip(("nst", "nfe", "nsetups", "netf", "nni", "ncfn", "nje", "nfeDQ", "qlast", "qcur"), io.tolist()))
+        d = dict(zip(("nst", "nfe", "nsetups", "netf", "nni", "ncfn", "nje", "nfeDQ", "qlast", "qcur"), io.tolist()))
+        d.update(zip(("hlast", "hcur", "hinused", "tcur"), ro.tolist()))
+        return d
 
     def __del__(self):
         try:

@@ -23,7 +23,7 @@ def emu():
     d = os.path.join(ROOT, "tests", "simt_emu")
     so = os.path.join(d, "libct_emu.so")
     srcs = [os.path.join(d, "emu_driver.cpp"), os.path.join(d, "simt_emu.h")] + [
-        os.path.join(ROOT, "chemtools_b200", "csrc", f) for f in ("kernels.cuh", "cti_parser.cpp", "mech_compile.cpp", "mechanism.hpp")]
+        os.path.join(ROOT, "chemtools_b200", "csrc", f) for f in ("kernels.cuh", "cti_parser.cpp", "mech_compile.cpp", "mechanism.hpp", "mech_shapes.inc")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-D__align__(x)=alignas(x)", "-o", so,
                                srcs[0], srcs[3], srcs[4]])
@@ -38,6 +38,9 @@ def emu():
                                 C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, lp, ip, C.c_int,
                                 C.c_int, C.c_double, C.c_int, C.c_int, dp]
     L.emu_roberts.argtypes = [C.c_int, dp, C.c_double, dp, dp, lp]
+    L.emu_set_stats_ex_buffer.argtypes = [dp]
+    L.emu_static_shape.argtypes = [C.c_void_p]
+    L.emu_use_static_shapes.argtypes = [C.c_int]
     return L
 
 
@@ -92,6 +95,36 @@ def test_rhs_kernel_source_vs_oracle(emu, emech, omech, name):
         assert (np.abs(qf2 - qf) / (np.abs(qf) + 1e-300)).max() < 1e-12
         assert (np.abs(qr2 - qr) / (np.abs(qr) + 1e-300)).max() < 1e-12
         assert (np.abs(yd2 - yd) / np.abs(yd).max(1, keepdims=True)).max() < 1e-12
+
+
+@pytest.mark.parametrize("name,shape", [("gri30", 1), ("gri211", 2), ("gri12", 3)])
+def test_static_shapes_match_the_mechanism_compiler(emu, emech, omech, name, shape):
+    """chemtools_b200/csrc/mech_shapes.inc (sizes and blob offsets as compile-time constants, generated at build time) is
+    what the mechanism compiler produces for the shipped mechanisms, and the specialised instantiations give the same
+    bits as the run-time shape: right-hand side with rates, and a fused integration (pool layout, two warps)."""
+    om, h = omech(name), emech(name)
+    assert emu.emu_static_shape(h) == shape
+    rng = np.random.default_rng(5)
+    n, K = 3, om.K
+    T0 = rng.uniform(900, 2500, n); p0 = rng.uniform(0.5, 20, n) * 101325
+    T0[0] = 350.0
+    Y = rng.random((n, K)) ** 4
+    Y /= Y.sum(1, keepdims=True)
+    st = np.ascontiguousarray(np.concatenate([T0[:, None], Y], 1))
+    out = []
+    try:
+        for static in (0, 1):
+            emu.emu_use_static_shapes(static)
+            yd, wd, qf, qr = np.zeros((n, K + 1)), np.zeros((n, K)), np.zeros((n, om.nR)), np.zeros((n, om.nR))
+            emu.emu_rhs(h, 0, n, P(T0), P(p0), P(np.ascontiguousarray(Y)), P(st), P(yd), P(wd), P(qf), P(qr))
+            Yf = om.X_to_Y(om.composition({"H2": 2.0, "O2": 1.0, "N2": 3.76}))
+            r = _integrate(emu, h, om, 1, [1250.0, 1100.0], [101325.0, 2e5], np.stack([Yf, Yf]), 1e-8, 1e-14, 4e-5, linsol=1, warps=2, pool_n=1)
+            out.append((yd, wd, qf, qr, r["state"], r["stats"], r["tau"]))
+    finally:
+        emu.emu_use_static_shapes(0)
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert np.all(out[0][5][:, 0] > 20)
 
 
 @pytest.mark.parametrize("mode", [0, 1])
@@ -158,6 +191,43 @@ def test_fused_integrator_source_vs_oracle(emu, emech, omech, goldens):
     assert np.abs(r["traj"][0, :, 0] / ref["traj"][0, :, 0] - 1).max() < 1e-4
     assert abs(r["tau"][0] / ref["tau"][0] - 1) < 1e-4
     assert abs(r["stats"][0, 0] / ref["stats"][0, 0] - 1) < 0.25  # step counts stay statistically close to CVODE's
+
+
+def test_extended_statistics_vs_oracle(emu, emech, omech, oracle, goldens):
+    """MainSolverStatistics beyond the counters (include/sundials/cvode/types.hpp:175-215 of the reference: last / current
+    order, first / last / next step size, current time).  On the CVODE Roberts problem the device stepper and the oracle
+    take the same steps over the first three outputs (later, last-bit differences move the step sequence), so every entry must agree there; on a reactor (where last-bit differences move the step sequence)
+    the first step, the current time and the ranges are checked."""
+    g = goldens["roberts"]
+    t = np.array(g["t_out"][:3]); atol = np.array(g["atol"])
+    y = np.zeros((3, 3)); st = np.zeros(8, dtype=np.int64); ex = np.zeros(6)
+    emu.emu_set_stats_ex_buffer(P(ex))
+    assert emu.emu_roberts(3, P(t), g["rtol"], P(atol), P(y), st.ctypes.data_as(lp)) == 0
+    f = lambda tt, yy: np.array([-0.04 * yy[0] + 1e4 * yy[1] * yy[2], 0.04 * yy[0] - 1e4 * yy[1] * yy[2] - 3e7 * yy[1] ** 2, 3e7 * yy[1] ** 2])
+    jac = lambda tt, yy: np.array([[-0.04, 1e4 * yy[2], 1e4 * yy[1]], [0.04, -1e4 * yy[2] - 6e7 * yy[1], -1e4 * yy[1]], [0.0, 6e7 * yy[1], 0.0]])
+    o = oracle.BDF(3, f, jac)
+    o.init(0.0, g["y0"], g["rtol"], atol)
+    for tk in t:
+        assert o.integrate(tk)[0] == 0
+    so = o.stats()
+    assert [int(ex[0]), int(ex[1])] == [so["qlast"], so["qcur"]]
+    assert np.abs(ex[2:6] / np.array([so["hinused"], so["hlast"], so["hcur"], so["tcur"]]) - 1).max() < 1e-4, (ex, so)
+    assert int(st[0]) == so["nst"]
+    om, h = omech("gri12"), emech("gri12")
+    n = 2
+    T0 = np.array([1150.0, 1400.0]); p0 = np.full(n, 2 * 101325.0)
+    Y = np.ascontiguousarray(om.X_to_Y(np.tile(om.composition({"H2": 2, "O2": 1, "N2": 3.76}), (n, 1))))
+    ref = om.integrate_batch(1, T0, p0, Y, 2e-4, rtol=1e-8, atol=1e-14, max_steps=20000)
+    ex = np.zeros((n, 6))
+    emu.emu_set_stats_ex_buffer(P(ex))
+    r = _integrate(emu, h, om, 1, T0, p0, Y, 1e-8, 1e-14, 2e-4, jac=0, linsol=0)
+    assert np.array_equal(r["status"], ref["status"])
+    ex_ref = ref["stats_ex"]
+    assert np.abs(ex[:, 2] / ex_ref[:, 2] - 1).max() < 1e-9                  # first step size: same state, same heuristic
+    assert np.array_equal(ex[:, 5], ex_ref[:, 5]) and np.all(ex[:, 5] == 2e-4)  # current time = stop time
+    assert np.all((ex[:, :2] >= 1) & (ex[:, :2] <= 5)) and np.all(np.abs(ex[:, :2] - ex_ref[:, :2]) <= 1)
+    assert np.all((ex[:, 3:5] > 0) & (ex[:, 3:5] < 2e-4))
+    assert np.abs(r["stats"][:, 0] / ref["stats"][:, 0] - 1).max() < 0.05
 
 
 def test_work_queue_resume_and_failure_codes(emu, emech, omech):

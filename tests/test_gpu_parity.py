@@ -8,6 +8,8 @@ Tolerances (BASELINE.json north_star):
       for species in balance) and additionally per reaction on qf, qr themselves.
   temperature trajectories and ignition delay  1e-4 relative at matched rtol/atol.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -45,6 +47,16 @@ def _ch4_air(chem, phi):
     X[:, chem.speciesIndex("O2")] = 2.0
     X[:, chem.speciesIndex("N2")] = 7.52
     return chem.mass_fractions(X)
+
+
+def _specific_energy(om, T, Y, internal):
+    """Mass-specific enthalpy (or internal energy) of n mixtures from the oracle's NASA-7 evaluation [J/kg]."""
+    out = np.zeros(len(T))
+    for i in range(len(T)):
+        _, h, _ = om.species_thermo(float(T[i]))  # J/kmol
+        e = h - om.R * T[i] if internal else h
+        out[i] = np.dot(Y[i] / om.W, e)
+    return out
 
 
 @pytest.mark.parametrize("name", ["gri30", "gri211", "gri12"])
@@ -346,7 +358,7 @@ def test_table_reactor_integration(ctb, chem, omech, tmp_path):
     assert b3.Integrate(t_end) >= 0 and b4.Integrate(t_end) >= 0 and np.array_equal(b3.MassFractions(), b4.MassFractions())
 
 
-def test_full_size_properties(ctb, chem):
+def test_full_size_properties(ctb, chem, omech):
     """BASELINE config 2 at full size (4096 reactors): size-independent invariants — mass fractions sum to one,
     element mass is conserved, constant-volume adiabatic reactors conserve internal energy, tau is monotone in T0
     at fixed phi on the igniting branch."""
@@ -360,6 +372,12 @@ def test_full_size_properties(ctb, chem):
     assert code >= 0
     Y = b.MassFractions()
     assert np.abs(Y.sum(1) - 1).max() < 1e-7
+    # closed adiabatic constant-volume reactor: the specific internal energy is an invariant of the exact solution
+    om = omech("gri30")
+    sub = np.arange(0, 4096, 8)
+    u0 = _specific_energy(om, T0[sub], Y0[sub], True); u1 = _specific_energy(om, b.Temperature()[sub], Y[sub], True)
+    scale = np.abs(_specific_energy(om, T0[sub], Y0[sub], False) - u0).max()  # p / rho, the natural energy scale
+    assert np.abs(u1 - u0).max() / scale < 1e-5
     W = ch.getMolecularWeights()
     nel = len(ch.elements())
     A = np.array([[ch.nAtoms(k, e) for e in range(nel)] for k in range(ch.n_species)])
@@ -481,30 +499,33 @@ def test_retry_of_crawling_reactors(ctb, chem, omech):
 
 
 @pytest.mark.parametrize("mech", ["gri12", "gri211"])
-def test_config3_full_size_properties(ctb, chem, mech):
-    """BASELINE config 3 at full size (65 536 constant-pressure CH4/air reactors, randomised T0 / p / phi): mass
-    fractions sum to one, element mass and (constant pressure, adiabatic) specific enthalpy are conserved, and at most
-    0.2 % of the reactors end with a negative CVODE status (the crawl of DESIGN.md section 3 item 5, which the reference's
-    algorithm shows at the same rate)."""
+def test_config3_full_size_properties(ctb, chem, omech, mech):
+    """BASELINE config 3 at full size (65 536 constant-pressure CH4/air reactors, randomised T0 / p / phi) through
+    ct_batch_integrate_with_retry: every reactor reaches the stop time (the few that crawl into CV_TOO_MUCH_WORK /
+    CV_ERR_FAILURE in the first pass, DESIGN.md, are recovered by the library), mass fractions sum to one, element mass
+    and (constant pressure, adiabatic) specific enthalpy are conserved."""
     from chemtools_b200 import workloads as W
-    ch = chem(mech)
+    ch, om = chem(mech), omech(mech)
     _, rt, T0, p0, X, t_end, _ = W.config3(ch, mech, 65536, 20211)
     Y0 = ch.mass_fractions(X)
     b = ctb.ReactorBatch(rt, ch, T0, p0, Y0, 1e-8, 1e-14, t_end, max_num_steps=50000)
-    b.Integrate(t_end)
-    status = b.Status()
-    ok = status >= 0
-    assert (~ok).mean() <= 0.002
-    Y = b.MassFractions()[ok]
+    res = b.IntegrateWithRetry()
+    print("config3 %s: %d of 65536 reactors failed in the first pass, %d after the retry" % (mech, res["failed_first"], res["failed_final"]))
+    assert res["failed_first"] <= 131 and res["failed_final"] == 0 and np.all(res["status"] >= 0) and res["code"] >= 0
+    Y = b.MassFractions()
     assert np.abs(Y.sum(1) - 1).max() < 1e-7
     Wk = ch.getMolecularWeights()
     nel = len(ch.elements())
     A = np.array([[ch.nAtoms(k, e) for e in range(nel)] for k in range(ch.n_species)])
-    el0, el1 = (Y0[ok] / Wk) @ A, (Y / Wk) @ A
+    el0, el1 = (Y0 / Wk) @ A, (Y / Wk) @ A
     assert np.abs(el1 - el0).max() / np.abs(el0).max() < 1e-7
-    assert np.allclose(b.Time()[ok], t_end)
-    T = b.Temperature()[ok]
-    assert T.min() > 900.0 and T.max() < 3500.0 and (T > T0[ok] + 400).mean() > 0.3  # a good part has ignited
+    assert np.allclose(b.Time(), t_end)
+    T = b.Temperature()
+    assert T.min() > 900.0 and T.max() < 3500.0 and (T > T0 + 400).mean() > 0.3  # a good part has ignited
+    sub = np.arange(0, 65536, 64)
+    h0 = _specific_energy(om, T0[sub], Y0[sub], False); h1 = _specific_energy(om, T[sub], Y[sub], False)
+    scale = np.abs(h0 - _specific_energy(om, T0[sub], Y0[sub], True)).max()  # R T / W, the natural energy scale
+    assert np.abs(h1 - h0).max() / scale < 1e-5
 
 
 def test_config4_and_config5_large_slices(ctb, chem):
@@ -520,9 +541,9 @@ def test_config4_and_config5_large_slices(ctb, chem):
     Y0 = ch.mass_fractions(X)
     b = ctb.ReactorBatch(rt, ch, Ta, pa, Y0, 1e-8, 1e-14, t_end, max_num_steps=50000)
     b.SetTable(*extra["table"])
-    b.Integrate(t_end)
+    res = b.IntegrateWithRetry()
     ok = b.Status() >= 0
-    assert (~ok).mean() <= 0.002
+    assert res["failed_first"] <= 65 and res["failed_final"] == 0 and ok.all()
     Y = b.MassFractions()[ok]
     assert np.abs(Y.sum(1) - 1).max() < 1e-7
     el0, el1 = (Y0[ok] / Wk) @ A, (Y / Wk) @ A
@@ -536,9 +557,9 @@ def test_config4_and_config5_large_slices(ctb, chem):
     phi = np.linspace(0.5, 2.0, 256)[iphi]
     Y0 = ch.mass_fractions(W._fill(ch, len(T0), {"CH4": phi, "O2": 2.0, "N2": 7.52}))
     c = ctb.ReactorBatch(ctb.Type.Const_Pres, ch, T0, p0, Y0, 1e-8, 1e-14, 1e-3, max_num_steps=50000)
-    c.Integrate(1e-3)
+    res = c.IntegrateWithRetry()
     ok = c.Status() >= 0
-    assert (~ok).mean() <= 0.002
+    assert res["failed_first"] <= 32 and res["failed_final"] == 0 and ok.all()
     Y = c.MassFractions()
     assert np.abs(Y[ok].sum(1) - 1).max() < 1e-7
     el0, el1 = (Y0[ok] / Wk) @ A, (Y[ok] / Wk) @ A
@@ -546,6 +567,70 @@ def test_config4_and_config5_large_slices(ctb, chem):
     tau = np.where(ok, c.IgnitionDelay(), np.nan).reshape(32, 512)
     both = np.isfinite(tau[:-1]) & np.isfinite(tau[1:])
     assert both.sum() > 2000 and (tau[1:][both] < tau[:-1][both]).mean() > 0.995  # hotter ignites earlier
+
+
+def test_extended_statistics_and_vector_tolerances(ctb, chem, omech):
+    """ct_batch_get_stats_ex (MainSolverStatistics: last / current order, first / last / next step, current time;
+    include/sundials/cvode/types.hpp:175-215, src/sundials/cvode/interface.cpp:487-560 of the reference) and
+    ct_batch_set_tolerances_vec (Client::SetTolerances with a vector, client.hpp:122-134) against the oracle."""
+    ch, om = chem("gri30"), omech("gri30")
+    n = 8
+    T0 = np.linspace(1050.0, 1400.0, n); p0 = np.full(n, 101325.0)
+    Y0 = _h2_air(ch, T0, np.full(n, 1.0))
+    ref = om.integrate_batch(1, T0, p0, Y0, 1e-3, rtol=1e-8, atol=1e-14, max_steps=50000, nthreads=8)
+    b = ctb.ReactorBatch(1, ch, T0, p0, Y0, 1e-8, 1e-14, 1e-3, max_num_steps=50000)
+    assert b.Integrate(1e-3) >= 0
+    ex, exo = b.StatisticsEx(), ref["stats_ex"]
+    assert np.abs(ex[:, 2] / exo[:, 2] - 1).max() < 1e-6              # first step: same state, same heuristic
+    assert np.array_equal(ex[:, 5], np.full(n, 1e-3))                 # current time = stop time
+    assert np.all((ex[:, :2] >= 1) & (ex[:, :2] <= 5)) and np.abs(ex[:, :2] - exo[:, :2]).max() <= 2
+    assert np.all((ex[:, 3:5] > 0) & (ex[:, 3:5] < 1e-3))
+    lo, hi = np.minimum(ex[:, 3], exo[:, 3]), np.maximum(ex[:, 3], exo[:, 3])
+    assert np.median(hi / lo) < 3.0                                   # last step sizes of the same order
+    # a CV_SUCCESS return before the stop time: the integrator is beyond the output time, the next step is planned
+    c = ctb.ReactorBatch(1, ch, T0, p0, Y0, 1e-8, 1e-14, 1e-3, max_num_steps=50000)
+    assert c.Integrate(2e-4) == 0
+    e2 = c.StatisticsEx()
+    assert np.all(e2[:, 5] >= 2e-4) and np.all(e2[:, 5] - e2[:, 3] < 2e-4 + 1e-12) and np.all(e2[:, 4] > 0)
+    assert np.array_equal(c.Time(), np.full(n, 2e-4))
+    # vector absolute tolerances: all entries equal reproduces the scalar run bit for bit; a loose temperature entry
+    # changes the step sequence but not the answer
+    v = ctb.ReactorBatch(1, ch, T0, p0, Y0, 1e-8, 1e-14, 1e-3, max_num_steps=50000)
+    v.SetTolerances(1e-8, np.full(v.n_state, 1e-14))
+    assert v.Integrate(1e-3) >= 0
+    assert np.array_equal(v.Solution(), b.Solution()) and np.array_equal(v.Statistics(), b.Statistics())
+    atol = np.full(v.n_state, 1e-14); atol[0] = 1e-6
+    w = ctb.ReactorBatch(1, ch, T0, p0, Y0, 1e-8, 1e-14, 1e-3, max_num_steps=50000)
+    w.SetTolerances(1e-8, atol)
+    assert w.Integrate(1e-3) >= 0
+    refv = om.integrate_batch(1, T0, p0, Y0, 1e-3, rtol=1e-8, atol=1e-14, max_steps=50000, nthreads=8)
+    assert np.abs(w.Temperature() / refv["state"][:, 0] - 1).max() < 1e-4
+    with pytest.raises(ctb.reactors.CtError):
+        w.SetTolerances(1e-8, -atol)
+    with pytest.raises(ctb.reactors.CtError):
+        w.SetMaxNumSteps(-5)
+    # a second Integrate after CV_TOO_MUCH_WORK goes on with a fresh step budget (CVode called again), like the reference's loop
+    t = ctb.ReactorBatch(1, ch, T0[:2], p0[:2], Y0[:2], 1e-8, 1e-14, 1e-3, max_num_steps=300)
+    codes = [t.Integrate(1e-3) for _ in range(12)]
+    assert codes[0] == -1 and codes[-1] in (0, 1) and np.allclose(t.Time(), 1e-3)
+    assert np.abs(t.Temperature() / ref["state"][:2, 0] - 1).max() < 1e-4
+    with pytest.raises(ctb.reactors.CtError):
+        t.SetOrder(np.array([0, 0], dtype=np.int32))  # not a permutation
+
+
+def test_cxx_binding(ctb, tmp_path):
+    """include/chemtools_b200.hpp (the C++14 GpuBatch binding of INTEGRATION.md) compiled with g++ -std=c++14 against
+    libchemtools_b200.so and run: the reference's reactor test (tests/src/reactor.cpp:50-140) with its own control
+    flow and assertions, the Set* validation, vector tolerances and the retry entry point."""
+    import subprocess
+    from conftest import ROOT
+    exe = str(tmp_path / "gpu_batch_test")
+    libdir = os.path.join(ROOT, "chemtools_b200")
+    subprocess.check_call(["g++", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "cxx", "gpu_batch_test.cpp"), "-L" + libdir, "-lchemtools_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe, ctb.mechanism_path("gri30")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "ignition 3.1" in out.stdout and "ensemble tau" in out.stdout
 
 
 def test_empty_and_error_paths(ctb, chem):

@@ -127,3 +127,24 @@ def test_no_cpu_fallback_without_device(ctb, chem):
     assert e.value.code == -102
     with pytest.raises(ctb.reactors.CtError):
         ctb.measure_fp64_peak()
+
+
+def test_cxx_binding_compiles_and_links(ctb, tmp_path):
+    """include/chemtools_b200.hpp + tests/cxx/gpu_batch_test.cpp (the C++14 GpuBatch binding of INTEGRATION.md) build with
+    g++ -std=c++14 -Wall -Wextra -Werror against the library; without a GPU the program fails loudly (no CPU path)."""
+    import subprocess
+    exe = str(tmp_path / "gpu_batch_test")
+    libdir = os.path.join(ROOT, "chemtools_b200")
+    subprocess.check_call(["g++", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "cxx", "gpu_batch_test.cpp"), "-L" + libdir, "-lchemtools_b200", "-Wl,-rpath," + libdir])
+    if ctb.device_count() > 0:
+        pytest.skip("a CUDA device is present: the program itself runs in the GPU tier (test_cxx_binding)")
+    out = subprocess.run([exe, ctb.mechanism_path("gri30")], capture_output=True, text=True, timeout=120)
+    assert out.returncode != 0 and "no CUDA device" in out.stderr
+
+
+@pytest.mark.parametrize("name,shape", [("gri30", 1), ("gri211", 2), ("gri12", 3)])
+def test_static_shapes_cover_the_shipped_mechanisms(chem, name, shape):
+    """mech_shapes.inc (generated at build time from the mechanism compiler) matches what the library compiles from the
+    shipped mechanisms: the specialised kernels are selected for them."""
+    assert chem(name).static_shape() == shape
