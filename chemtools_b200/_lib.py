@@ -123,6 +123,23 @@ def lib():
         "ct_batch_last_kernel_ms": (dbl, [vp]),
         "ct_batch_launch_count": (i64, [vp]),
         "ct_batch_warps_per_sm": (i32, [vp]),
+        "ct_host_alloc": (i32, [i64, C.POINTER(vp)]),
+        "ct_host_free": (i32, [vp]),
+        "ct_ensemble_create": (vp, [vp, i32, i64, i32, ip, C.POINTER(C.c_int)]),
+        "ct_ensemble_destroy": (None, [vp]),
+        "ct_ensemble_n_shards": (i32, [vp]),
+        "ct_ensemble_set_partition": (i32, [vp, i32, i64]),
+        "ct_ensemble_set_tolerances": (i32, [vp, dbl, dbl]),
+        "ct_ensemble_set_stop_time": (i32, [vp, dbl]),
+        "ct_ensemble_set_max_steps": (i32, [vp, i64]),
+        "ct_ensemble_set_retry": (i32, [vp, i32]),
+        "ct_ensemble_set_hot_first": (i32, [vp, i32]),
+        "ct_ensemble_set_configure": (i32, [vp, vp, vp]),
+        "ct_ensemble_set_tp_table": (i32, [vp, i32, dp, dp, dp]),
+        "ct_partition_range": (i32, [i64, i32, i32, i32, lp, lp, lp]),
+        "ct_ensemble_shard_range": (i32, [vp, i32, lp, lp, lp]),
+        "ct_ensemble_integrate": (i32, [vp, vp, vp, vp, vp, vp, vp, vp]),
+        "ct_ensemble_shard_info": (i32, [vp, i32, lp, dp]),
         "ct_rhs_eval": (i32, [vp, dp, dp, dp, dp, dp, dp]),
         "ct_jacobian_eval": (i32, [vp, i32, dp, dp, dp]),
         "ct_lu_solve": (i32, [i32, i64, dp, dp, dp, ip, i32]),

@@ -3,13 +3,16 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/chemtools_b200.h"
@@ -110,12 +113,14 @@ struct ct_mech {
   MechDesc desc{};
   int shape = 0;  // static_shape_of(desc)
   std::map<int, std::pair<unsigned char*, int*>> dev;  // device ordinal -> (blob, perm)
+  std::mutex mu;  // batches on several devices may be driven from several host threads (ct_ensemble)
   ~ct_mech() {
     for (auto& kv : dev) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
   }
   int on_device(const unsigned char** blob, const int** perm) {
     int d = 0;
     CT_CUDA(cudaGetDevice(&d));
+    std::lock_guard<std::mutex> lock(mu);
     auto it = dev.find(d);
     if (it == dev.end()) {
       unsigned char* b = nullptr;
@@ -1231,3 +1236,5 @@ int ct_roberts_selftest(int n_out, const double* t_out, double rtol, const doubl
 }
 
 }  // extern "C"
+
+#include "ensemble.inl"

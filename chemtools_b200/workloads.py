@@ -3,9 +3,19 @@
 Pure host-side input generation (numpy); every generator returns
 (mechanism name, reactor Type, T0[n], p0[n], X[n, K] mole fractions, t_end, extra).
 """
+import enum
+
 import numpy as np
 
-from .reactors import Type
+try:
+    from .reactors import Type
+except ImportError:  # loaded as a plain file (bench.py --impl reference: numpy only, the CUDA library stays unmapped)
+    class Type(enum.IntEnum):
+        Const_Pres = 0
+        Const_Vol = 1
+        Const_Temp_Pres = 2
+        Const_Temp_Vol = 3
+        Table_Temp_Pres = 4
 
 ONE_ATM = 101325.0
 
@@ -22,11 +32,15 @@ def config1(chem):
     return "gri30", Type.Const_Pres, np.array([1200.0]), np.array([ONE_ATM]), _fill(chem, 1, {"CH4": 1.0, "O2": 2.0, "N2": 7.52}), 1e-1, {}
 
 
-def config2(chem, n_side=64):
-    """ConstVol H2/air ignition-delay sweep, GRI-3.0, n_side^2 reactors over T0=900-1500 K x phi=0.5-2.0."""
-    T0 = np.repeat(np.linspace(900.0, 1500.0, n_side), n_side)
-    phi = np.tile(np.linspace(0.5, 2.0, n_side), n_side)
-    n = n_side * n_side
+def config2(chem, n_side=64, n_phi=None, index=None):
+    """ConstVol H2/air ignition-delay sweep, GRI-3.0, n_side x n_phi reactors over T0=900-1500 K x phi=0.5-2.0
+    (n_phi = n_side by default); `index` selects reactors of that global sweep (a shard)."""
+    n_phi = n_side if n_phi is None else n_phi
+    T0 = np.repeat(np.linspace(900.0, 1500.0, n_side), n_phi)
+    phi = np.tile(np.linspace(0.5, 2.0, n_phi), n_side)
+    if index is not None:
+        T0, phi = T0[index], phi[index]
+    n = len(T0)
     return "gri30", Type.Const_Vol, T0, np.full(n, ONE_ATM), _fill(chem, n, {"H2": 2.0 * phi, "O2": 1.0, "N2": 3.76}), 1e-3, {"phi": phi}
 
 
@@ -53,14 +67,29 @@ def config4(chem, n=262144, nt=101, seed=30):
     return "gri30", Type.Table_Temp_Pres, Ta, pa, _fill(chem, n, {"CH4": phi, "O2": 2.0, "N2": 7.52}), t_end, {"table": (tt, tabT, tabp), "phi": phi}
 
 
-def config5_slice(chem, lo, hi, n_side=256):
-    """Reactors [lo, hi) of the 256^3 ConstPres GRI-3.0 CH4/air ignition-delay map (T0 x p x phi)."""
-    idx = np.arange(lo, hi)
+def config5_index(chem, idx, n_side=256):
+    """Reactors idx[] of the 256^3 ConstPres GRI-3.0 CH4/air ignition-delay map (T0 x p x phi, phi fastest)."""
+    idx = np.asarray(idx, dtype=np.int64)
     iT, ip, iphi = idx // (n_side * n_side), (idx // n_side) % n_side, idx % n_side
     T0 = np.linspace(1000.0, 2000.0, n_side)[iT]
     p0 = np.geomspace(1.0, 40.0, n_side)[ip] * ONE_ATM
     phi = np.linspace(0.5, 2.0, n_side)[iphi]
-    return "gri30", Type.Const_Pres, T0, p0, _fill(chem, hi - lo, {"CH4": phi, "O2": 2.0, "N2": 7.52}), 1e-3, {"phi": phi}
+    return "gri30", Type.Const_Pres, T0, p0, _fill(chem, len(idx), {"CH4": phi, "O2": 2.0, "N2": 7.52}), 1e-3, {"phi": phi}
+
+
+def config5_design(n, n_side=256):
+    """n global reactor indices spread over the whole 256^3 map: a 3-D Kronecker (additive-recurrence) sequence, so that
+    every prefix and every strided subset covers all of T0, p and phi alike (a plain stride of 2^k would pin phi)."""
+    g = 1.22074408460575947536  # real root of x^4 = x + 1: the 3-D analogue of the golden ratio
+    al = np.array([1.0 / g, 1.0 / g ** 2, 1.0 / g ** 3])
+    k = np.arange(1, n + 1, dtype=np.float64)[:, None]
+    c = np.floor(((0.5 + k * al[None, :]) % 1.0) * n_side).astype(np.int64)
+    return c[:, 0] * n_side * n_side + c[:, 1] * n_side + c[:, 2]
+
+
+def config5_slice(chem, lo, hi, n_side=256):
+    """Reactors [lo, hi) of the 256^3 ConstPres GRI-3.0 CH4/air ignition-delay map (T0 x p x phi)."""
+    return config5_index(chem, np.arange(lo, hi), n_side)
 
 
 def shard_range(n, rank, world):

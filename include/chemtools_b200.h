@@ -224,6 +224,46 @@ double ct_batch_last_kernel_ms(const ct_batch*);
 int64_t ct_batch_launch_count(const ct_batch*);
 int ct_batch_warps_per_sm(const ct_batch*);
 
+/* ---- multi-GPU ensembles (no reference counterpart: Base::Solve, src/applications/reactors/
+ * base.cpp:123-170, integrates one reactor on one host thread).  Reactors are independent, so n reactors are partitioned
+ * over the listed devices of one box: one host thread + one CUDA stream per device, each shard processed as a sequence
+ * of ordinary batches of at most `chunk` reactors, no collective on the solve path; every device copies its results with
+ * cudaMemcpyAsync D2H into disjoint slices of the caller's host arrays (the final gather for the HDF5 writer,
+ * src/results/hdf5_writer.cpp:101-110).  Bit-identical to one batch on one device. */
+typedef struct ct_ensemble ct_ensemble;
+enum { CT_PARTITION_BLOCK = 0 /* reactor i -> shard floor(i*G/n), contiguous slices, results written in place */,
+       CT_PARTITION_CYCLIC = 1 /* reactor i -> shard i % G: every shard sees the same stiffness mix of a sorted sweep */ };
+/* called on every internal batch right after its creation: apply any ct_batch_set_* option; return < 0 to abort */
+typedef int (*ct_batch_configure_fn)(ct_batch*, void* user);
+/* page-locked host memory usable by every device (cudaHostAllocPortable): back the ensemble's input / output arrays with
+ * it and the per-device copies are true asynchronous DMA transfers */
+int ct_host_alloc(int64_t bytes, void** out);
+int ct_host_free(void* p);
+/* devices: n_devices ordinals (NULL = 0..n_devices-1; n_devices 0 = every visible device) */
+ct_ensemble* ct_ensemble_create(ct_mech*, int reactor_type, int64_t n, int n_devices, const int* devices, int* status);
+void ct_ensemble_destroy(ct_ensemble*);
+int ct_ensemble_n_shards(const ct_ensemble*);
+int ct_ensemble_set_partition(ct_ensemble*, int mode, int64_t chunk /* reactors per launch, 0 = keep (default 65536) */);
+int ct_ensemble_set_tolerances(ct_ensemble*, double rtol, double atol);
+int ct_ensemble_set_stop_time(ct_ensemble*, double t_end);
+int ct_ensemble_set_max_steps(ct_ensemble*, int64_t mxstep);
+int ct_ensemble_set_retry(ct_ensemble*, int on);      /* ct_batch_integrate_with_retry per chunk; default on */
+int ct_ensemble_set_hot_first(ct_ensemble*, int on);  /* queue each chunk hottest T0 first; default on (results unaffected) */
+int ct_ensemble_set_configure(ct_ensemble*, ct_batch_configure_fn fn, void* user);
+/* CT_TABLE_TP: common grid t[nt], T[n x nt], p[n x nt]; the arrays are borrowed until ct_ensemble_integrate returns */
+int ct_ensemble_set_tp_table(ct_ensemble*, int nt, const double* t, const double* T, const double* p);
+/* global reactor indices of a shard: first, first + stride, ... (count of them).  ct_partition_range is the same rule
+ * without a handle (host arithmetic only: callers that run one process per GPU use it to pick their slice) */
+int ct_partition_range(int64_t n, int n_shards, int mode, int shard, int64_t* first, int64_t* stride, int64_t* count);
+int ct_ensemble_shard_range(const ct_ensemble*, int shard, int64_t* first, int64_t* stride, int64_t* count);
+/* T[n], p[n], Y[n x K] -> state[n x N], tau[n] (NaN = not ignited), status[n], stats[n x 8] (any output may be NULL).
+ * Returns like ct_batch_integrate: 0 / 1 / the most negative per-reactor code; library errors (<= -100) name the shard */
+int ct_ensemble_integrate(ct_ensemble*, const double* T, const double* p, const double* Y, double* state, double* tau,
+                          int32_t* status, int64_t* stats);
+/* per shard after integrate: counts = reactors, chunks, kernel launches, failed before retry, failed after retry;
+ * times = sum of k_integrate device ms (CUDA events), wall seconds of the shard's host thread */
+int ct_ensemble_shard_info(const ct_ensemble*, int shard, int64_t counts[5], double times[2]);
+
 /* ---- stand-alone kernels (parity tests, ncu evidence) ---- */
 /* K1: Base/EnergyEnabled::RightHandSide for n states (host arrays). T0,p0,Y0 define the frozen quantities exactly
  * as Reactor::Create does; states n x N; outputs ydot n x N, wdot n x K [kmol/m^3/s], qf/qr n x R (file order; may

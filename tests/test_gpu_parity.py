@@ -53,8 +53,8 @@ def _specific_energy(om, T, Y, internal):
     """Mass-specific enthalpy (or internal energy) of n mixtures from the oracle's NASA-7 evaluation [J/kg]."""
     out = np.zeros(len(T))
     for i in range(len(T)):
-        _, h, _ = om.species_thermo(float(T[i]))  # J/kmol
-        e = h - om.R * T[i] if internal else h
+        _, h_RT, _ = om.species_thermo(float(T[i]))  # dimensionless h / (R T)
+        e = (h_RT - 1.0 if internal else h_RT) * om.R * T[i]  # J/kmol
         out[i] = np.dot(Y[i] / om.W, e)
     return out
 
