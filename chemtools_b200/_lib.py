@@ -133,6 +133,8 @@ def lib():
         "ct_ensemble_set_stop_time": (i32, [vp, dbl]),
         "ct_ensemble_set_max_steps": (i32, [vp, i64]),
         "ct_ensemble_set_retry": (i32, [vp, i32]),
+        "ct_ensemble_set_first_pass_steps": (i32, [vp, i64]),
+        "ct_ensemble_set_streams": (i32, [vp, i32]),
         "ct_ensemble_set_hot_first": (i32, [vp, i32]),
         "ct_ensemble_set_configure": (i32, [vp, vp, vp]),
         "ct_ensemble_set_tp_table": (i32, [vp, i32, dp, dp, dp]),

@@ -18,8 +18,8 @@ struct ct_ensemble {
   std::vector<int> devices;
   int partition = CT_PARTITION_BLOCK;
   double rtol = 1e-8, atol = 1e-14, t_stop = 1e-3;
-  int64_t mxstep = 500;
-  int retry = 1, hot_first = 1;
+  int64_t mxstep = 500, first_pass = 10000;
+  int retry = 1, hot_first = 1, streams = 2;
   ct_batch_configure_fn configure = nullptr;
   void* configure_user = nullptr;
   int nt = 0;
@@ -30,6 +30,16 @@ struct ct_ensemble {
     int rc = 0, worst = 0;
     bool all_tstop = true;
     std::string err;
+    std::vector<int64_t> bad;  // global indices of the reactors that ended with a negative status
+    std::mutex mu;
+    Shard() = default;
+    Shard(const Shard& o) : count(o.count), launches(o.launches), failed_first(o.failed_first), failed_final(o.failed_final), chunks(o.chunks),
+                            kernel_ms(o.kernel_ms), wall_s(o.wall_s), rc(o.rc), worst(o.worst), all_tstop(o.all_tstop), err(o.err), bad(o.bad) {}
+    Shard& operator=(const Shard& o) {
+      count = o.count; launches = o.launches; failed_first = o.failed_first; failed_final = o.failed_final; chunks = o.chunks;
+      kernel_ms = o.kernel_ms; wall_s = o.wall_s; rc = o.rc; worst = o.worst; all_tstop = o.all_tstop; err = o.err; bad = o.bad;
+      return *this;
+    }
   };
   std::vector<Shard> shards;
   int64_t shard_count(int g) const {
@@ -38,6 +48,10 @@ struct ct_ensemble {
     return (n * (g + 1) + G - 1) / G - (n * g + G - 1) / G;
   }
   // global index of the j-th reactor of shard g
+  // step budget of the chunk launches: a launch lasts as long as its slowest reactor (one warp, ~75 us per step), so the
+  // few reactors that need more than `first_pass` steps are cut off there and integrated again, with the full budget, in
+  // one batch per shard after its last chunk (one long tail per shard instead of one per chunk)
+  int64_t first_pass_budget() const { return (retry && first_pass > 0) ? std::min(first_pass, mxstep) : mxstep; }
   int64_t global_index(int g, int64_t j) const {
     const int64_t G = (int64_t)devices.size();
     if (partition == CT_PARTITION_CYCLIC) return g + j * G;
@@ -54,11 +68,24 @@ struct PinnedBuf {
   template <class T> T* as() { return static_cast<T*>(p); }
 };
 
-// one shard = one host thread, one device, one stream, a sequence of ordinary batches
-int run_shard(ct_ensemble* e, int g, const double* T, const double* p, const double* Y, double* state, double* tau,
-              int32_t* status, int64_t* stats) {
+int configure_batch(ct_ensemble* e, ct_batch* b, cudaStream_t stream, bool first_pass) {
+  b->stream = stream;
+  if (int r = ct_batch_set_tolerances(b, e->rtol, e->atol)) return r;
+  if (int r = ct_batch_set_stop_time(b, e->t_stop)) return r;
+  if (int r = ct_batch_set_max_steps(b, first_pass ? e->first_pass_budget() : e->mxstep)) return r;
+  if (e->configure) {
+    const int r = e->configure(b, e->configure_user);
+    if (r < 0) return r <= CT_ERR_INVALID ? r : fail(CT_ERR_INVALID, "configure callback failed");
+  }
+  return 0;
+}
+
+// one worker = one host thread, one stream on the shard's device, every `stride`-th chunk of the shard as a sequence of
+// ordinary batches.  Two workers per device keep two launches in flight: the CTAs of a launch leave as soon as the work
+// ring is empty, so the next chunk's CTAs take over the SMs while the last (slowest) reactors of this one finish.
+int run_worker(ct_ensemble* e, int g, int w, int stride, const double* T, const double* p, const double* Y, double* state, double* tau,
+               int32_t* status, int64_t* stats) {
   ct_ensemble::Shard& S = e->shards[g];
-  const auto t_begin = std::chrono::steady_clock::now();
   CT_CUDA(cudaSetDevice(e->devices[g]));
   cudaStream_t stream = nullptr;
   CT_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -79,20 +106,18 @@ int run_shard(ct_ensemble* e, int g, const double* T, const double* p, const dou
   }
   std::unique_ptr<ct_batch> batch;
   std::vector<int32_t> order, st_host;
-  for (int64_t c0 = 0; c0 < cnt; c0 += chunk) {
+  std::vector<int64_t> bad;
+  int64_t launches = 0, chunks = 0;
+  double kernel_ms = 0.0;
+  int worst = 0;
+  bool all_tstop = true;
+  for (int64_t c0 = (int64_t)w * chunk; c0 < cnt; c0 += (int64_t)stride * chunk) {
     const int64_t m = std::min<int64_t>(chunk, cnt - c0);
     if (!batch || batch->n != m) {
       int stc = 0;
       batch.reset(ct_batch_create(e->mech, e->rt, m, &stc));
       if (!batch) return stc;
-      batch->stream = stream;
-      if (int r = ct_batch_set_tolerances(batch.get(), e->rtol, e->atol)) return r;
-      if (int r = ct_batch_set_stop_time(batch.get(), e->t_stop)) return r;
-      if (int r = ct_batch_set_max_steps(batch.get(), e->mxstep)) return r;
-      if (e->configure) {
-        const int r = e->configure(batch.get(), e->configure_user);
-        if (r < 0) return r <= CT_ERR_INVALID ? r : fail(CT_ERR_INVALID, "configure callback failed");
-      }
+      if (int r = configure_batch(e, batch.get(), stream, true)) return r;
     }
     const double *cT, *cp, *cY, *cTabT = nullptr, *cTabp = nullptr;
     const int64_t i0 = e->global_index(g, c0);
@@ -112,6 +137,7 @@ int run_shard(ct_ensemble* e, int g, const double* T, const double* p, const dou
       cT = T + i0; cp = p + i0; cY = Y + i0 * K;
       if (nt) { cTabT = e->tab_T + i0 * nt; cTabp = e->tab_p + i0 * nt; }
     }
+    const int64_t launches_before = batch->launches + batch->aux_launches;
     if (int r = ct_batch_set_ic(batch.get(), cT, cp, cY)) return r;
     if (nt) { if (int r = ct_batch_set_tp_table(batch.get(), nt, e->tab_t, cTabT, cTabp)) return r; }
     if (e->hot_first && m > 1) {
@@ -121,14 +147,10 @@ int run_shard(ct_ensemble* e, int g, const double* T, const double* p, const dou
       std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return cT[a] > cT[b]; });
       if (int r = ct_batch_set_order(batch.get(), order.data())) return r;
     }
-    int64_t f1 = 0, f2 = 0;
-    const int64_t launches_before = batch->launches + batch->aux_launches;
-    int rc;
-    if (e->retry) rc = ct_batch_integrate_with_retry(batch.get(), &f1, &f2);
-    else rc = ct_batch_integrate(batch.get(), e->t_stop);
+    const int rc = ct_batch_integrate(batch.get(), e->t_stop);
     if (rc <= CT_ERR_INVALID) return rc;
-    S.kernel_ms += batch->last_ms; S.chunks += 1;
-    // results: plain cudaMemcpyAsync D2H on the shard's stream into the caller's slices (or the staging buffers)
+    kernel_ms += batch->last_ms; chunks += 1;
+    // results: plain cudaMemcpyAsync D2H on the worker's stream into the caller's slices (or the staging buffers)
     double* oState = state ? (cyclic ? sState.as<double>() : state + i0 * N) : nullptr;
     double* oTau = tau ? (cyclic ? sTau.as<double>() : tau + i0) : nullptr;
     int32_t* oStatus = status ? (cyclic ? sStatus.as<int32_t>() : status + i0) : nullptr;
@@ -140,14 +162,11 @@ int run_shard(ct_ensemble* e, int g, const double* T, const double* p, const dou
     CT_CUDA(cudaMemcpyAsync(oStatus ? oStatus : st_host.data(), batch->status.p, (size_t)m * 4, cudaMemcpyDeviceToHost, stream));
     CT_CUDA(cudaStreamSynchronize(stream));
     const int32_t* sv = oStatus ? oStatus : st_host.data();
-    int64_t nbad = 0;
     for (int64_t j = 0; j < m; ++j) {
-      if (sv[j] < S.worst) S.worst = sv[j];
-      if (sv[j] != CT_TSTOP_RETURN) S.all_tstop = false;
-      if (sv[j] < 0) ++nbad;
+      if (sv[j] < worst) worst = sv[j];
+      if (sv[j] != CT_TSTOP_RETURN) all_tstop = false;
+      if (sv[j] < 0) bad.push_back(e->global_index(g, c0 + j));
     }
-    if (!e->retry) { f1 = nbad; f2 = nbad; }
-    S.failed_first += f1; S.failed_final += f2;
     if (cyclic) {
       for (int64_t j = 0; j < m; ++j) {
         const int64_t i = e->global_index(g, c0 + j);
@@ -157,9 +176,80 @@ int run_shard(ct_ensemble* e, int g, const double* T, const double* p, const dou
         if (stats) std::memcpy(stats + i * 8, oStats + j * 8, 64);
       }
     }
-    S.launches += batch->launches + batch->aux_launches - launches_before;
+    launches += batch->launches + batch->aux_launches - launches_before;
   }
-  S.wall_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+  std::lock_guard<std::mutex> lock(S.mu);
+  S.launches += launches; S.chunks += chunks; S.kernel_ms += kernel_ms;
+  S.worst = std::min(S.worst, worst); S.all_tstop = S.all_tstop && all_tstop;
+  S.failed_first += (int64_t)bad.size();
+  S.bad.insert(S.bad.end(), bad.begin(), bad.end());
+  return 0;
+}
+
+// recovery pass of one shard, once, after all its chunks: the reactors that ended with a negative CVODE status are re-run
+// as one small batch, first with the full step budget (if the chunk launches had a smaller one), then under the ladder of
+// ct_batch_integrate_with_retry (Jacobian clip 1; LU instead of the inverse; difference-quotient Jacobian + LU), and the
+// successful ones overwrite their rows.  Same options, same ladder, same per-reactor arithmetic: identical to
+// ct_batch_integrate_with_retry on a single batch with the full budget.
+int run_ladder(ct_ensemble* e, int g, const double* T, const double* p, const double* Y, double* state, double* tau, int32_t* status,
+               int64_t* stats) {
+  ct_ensemble::Shard& S = e->shards[g];
+  std::vector<int64_t> bad = S.bad;
+  std::sort(bad.begin(), bad.end());
+  if (bad.empty()) { S.failed_final = 0; return 0; }
+  CT_CUDA(cudaSetDevice(e->devices[g]));
+  cudaStream_t stream = nullptr;
+  CT_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sg{stream};
+  const int K = e->K, N = e->N, nt = e->nt;
+  // rung 0: the caller's own options with the full step budget (only when the chunk launches ran with a smaller one)
+  for (int rung = (e->first_pass_budget() < e->mxstep) ? 0 : 1; rung < 4 && !bad.empty(); ++rung) {
+    const int64_t m = (int64_t)bad.size();
+    int stc = 0;
+    std::unique_ptr<ct_batch> r(ct_batch_create(e->mech, e->rt, m, &stc));
+    if (!r) return stc;
+    if (int rc = configure_batch(e, r.get(), stream, false)) return rc;
+    if (rung == 1) r->jac_clip = 1.0;
+    if (rung >= 2) r->linsol = LINSOL_LU;
+    if (rung == 3) r->jac_mode = CT_JAC_DQ;
+    std::vector<double> hT(m), hp(m), hY((size_t)m * K), hTabT, hTabp;
+    if (nt) { hTabT.resize((size_t)m * nt); hTabp.resize((size_t)m * nt); }
+    for (int64_t j = 0; j < m; ++j) {
+      const int64_t i = bad[j];
+      hT[j] = T[i]; hp[j] = p[i];
+      std::memcpy(hY.data() + j * K, Y + i * K, (size_t)K * 8);
+      if (nt) {
+        std::memcpy(hTabT.data() + j * nt, e->tab_T + i * nt, (size_t)nt * 8);
+        std::memcpy(hTabp.data() + j * nt, e->tab_p + i * nt, (size_t)nt * 8);
+      }
+    }
+    if (int rc = ct_batch_set_ic(r.get(), hT.data(), hp.data(), hY.data())) return rc;
+    if (nt) { if (int rc = ct_batch_set_tp_table(r.get(), nt, e->tab_t, hTabT.data(), hTabp.data())) return rc; }
+    const int rc = ct_batch_integrate(r.get(), e->t_stop);
+    if (rc <= CT_ERR_INVALID) return rc;
+    S.launches += r->launches + r->aux_launches;
+    std::vector<double> oState((size_t)m * N), oTau(m);
+    std::vector<int32_t> oStatus(m);
+    std::vector<int64_t> oStats((size_t)m * 8);
+    CT_CUDA(cudaMemcpyAsync(oState.data(), r->state.p, (size_t)m * N * 8, cudaMemcpyDeviceToHost, stream));
+    CT_CUDA(cudaMemcpyAsync(oTau.data(), r->tau.p, (size_t)m * 8, cudaMemcpyDeviceToHost, stream));
+    CT_CUDA(cudaMemcpyAsync(oStats.data(), r->stats.p, (size_t)m * 64, cudaMemcpyDeviceToHost, stream));
+    CT_CUDA(cudaMemcpyAsync(oStatus.data(), r->status.p, (size_t)m * 4, cudaMemcpyDeviceToHost, stream));
+    CT_CUDA(cudaStreamSynchronize(stream));
+    std::vector<int64_t> still;
+    for (int64_t j = 0; j < m; ++j) {
+      if (oStatus[j] < 0) { still.push_back(bad[j]); continue; }
+      const int64_t i = bad[j];
+      if (state) std::memcpy(state + i * N, oState.data() + j * N, (size_t)N * 8);
+      if (tau) tau[i] = oTau[j];
+      if (status) status[i] = oStatus[j];
+      if (stats) std::memcpy(stats + i * 8, oStats.data() + j * 8, 64);
+      if (oStatus[j] != CT_TSTOP_RETURN) S.all_tstop = false;
+    }
+    bad.swap(still);
+  }
+  S.failed_final = (int64_t)bad.size();
+  if (bad.empty()) S.worst = 0;
   return 0;
 }
 
@@ -224,7 +314,19 @@ int ct_ensemble_set_max_steps(ct_ensemble* e, int64_t mx) {
   e->mxstep = mx == 0 ? 500 : mx;
   return 0;
 }
+int ct_ensemble_set_first_pass_steps(ct_ensemble* e, int64_t steps) {
+  if (!e) return fail(CT_ERR_INVALID, "null ensemble");
+  if (steps < 0) return fail(CT_ILL_INPUT, "negative number of steps");
+  e->first_pass = steps;
+  return 0;
+}
 int ct_ensemble_set_retry(ct_ensemble* e, int on) { if (!e) return fail(CT_ERR_INVALID, "null ensemble"); e->retry = on ? 1 : 0; return 0; }
+int ct_ensemble_set_streams(ct_ensemble* e, int streams) {
+  if (!e) return fail(CT_ERR_INVALID, "null ensemble");
+  if (streams < 1 || streams > 4) return fail(CT_ERR_INVALID, "1 to 4 launches in flight per device");
+  e->streams = streams;
+  return 0;
+}
 int ct_ensemble_set_hot_first(ct_ensemble* e, int on) { if (!e) return fail(CT_ERR_INVALID, "null ensemble"); e->hot_first = on ? 1 : 0; return 0; }
 int ct_ensemble_set_configure(ct_ensemble* e, ct_batch_configure_fn fn, void* user) {
   if (!e) return fail(CT_ERR_INVALID, "null ensemble");
@@ -262,15 +364,38 @@ int ct_ensemble_integrate(ct_ensemble* e, const double* T, const double* p, cons
   int prev = 0;
   CT_CUDA(cudaGetDevice(&prev));
   for (int g = 0; g < G; ++g) { e->shards[g] = ct_ensemble::Shard(); e->shards[g].count = e->shard_count(g); }
-  std::vector<std::thread> th;
-  for (int g = 0; g < G; ++g) {
-    th.emplace_back([=]() {
-      ct_ensemble::Shard& S = e->shards[g];
-      S.rc = S.count > 0 ? run_shard(e, g, T, p, Y, state, tau, status, stats) : 0;
-      if (S.rc < 0) S.err = g_err;  // thread-local message of the worker
-    });
+  const auto t_begin = std::chrono::steady_clock::now();
+  {
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; ++g) {
+      const int64_t nchunks = (e->shards[g].count + e->chunk - 1) / std::max<int64_t>(e->chunk, 1);
+      const int W = (int)std::max<int64_t>(1, std::min<int64_t>(e->streams, nchunks));
+      for (int w = 0; w < W; ++w) {
+        th.emplace_back([=]() {
+          ct_ensemble::Shard& S = e->shards[g];
+          const int rc = S.count > 0 ? run_worker(e, g, w, W, T, p, Y, state, tau, status, stats) : 0;
+          if (rc < 0) { std::lock_guard<std::mutex> lock(S.mu); if (S.rc == 0) { S.rc = rc; S.err = g_err; } }  // thread-local message of the worker
+        });
+      }
+    }
+    for (auto& t : th) t.join();
   }
-  for (auto& t : th) t.join();
+  {
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; ++g) {
+      ct_ensemble::Shard& S = e->shards[g];
+      if (S.rc < 0) continue;
+      if (!e->retry || S.bad.empty()) { S.failed_final = S.failed_first; continue; }
+      th.emplace_back([=]() {
+        ct_ensemble::Shard& Sg = e->shards[g];
+        const int rc = run_ladder(e, g, T, p, Y, state, tau, status, stats);
+        if (rc < 0) { Sg.rc = rc; Sg.err = g_err; }
+      });
+    }
+    for (auto& t : th) t.join();
+  }
+  const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+  for (int g = 0; g < G; ++g) e->shards[g].wall_s = wall;
   cudaSetDevice(prev);
   int worst = 0;
   bool all_tstop = true, any = false;

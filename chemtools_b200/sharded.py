@@ -108,6 +108,14 @@ class Ensemble:
     def SetRetry(self, on):
         check(lib().ct_ensemble_set_retry(self._h, int(bool(on))))
 
+    def SetFirstPassSteps(self, n):
+        """Step budget of the chunk launches (the recovery pass re-runs the few longer reactors with the full budget)."""
+        check(lib().ct_ensemble_set_first_pass_steps(self._h, int(n)))
+
+    def SetStreams(self, n):
+        """Launches in flight per device (the tail of one chunk overlaps the next chunk); default 2."""
+        check(lib().ct_ensemble_set_streams(self._h, int(n)))
+
     def SetHotFirst(self, on):
         check(lib().ct_ensemble_set_hot_first(self._h, int(bool(on))))
 
@@ -157,7 +165,9 @@ class Ensemble:
         status = buf("status", (self.n,), np.int32)
         stats = buf("stats", (self.n, 8), np.int64, want_stats)
         ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
-        code = check(lib().ct_ensemble_integrate(self._h, ptr(T), ptr(p), ptr(Y), ptr(state), ptr(tau), ptr(status), ptr(stats)))
+        code = lib().ct_ensemble_integrate(self._h, ptr(T), ptr(p), ptr(Y), ptr(state), ptr(tau), ptr(status), ptr(stats))
+        if code <= -20:  # call-level error (CT_ILL_INPUT, library errors); -1 ... -6 are per-reactor CVODE codes (the worst of them), results not errors
+            check(code)
         shards = []
         for g in range(self.n_shards()):
             counts = np.zeros(5, dtype=np.int64); times = np.zeros(2)
@@ -170,12 +180,16 @@ class Ensemble:
 
 
 def integrate(chemistry, reactor_type, T, p, Y, rtol=1e-8, atol=1e-14, t_end=1e-3, devices=None, max_num_steps=20000,
-              partition="block", chunk=0, retry=True, table=None, configure=None, want_state=True, want_stats=True):
+              partition="block", chunk=0, retry=True, table=None, configure=None, want_state=True, want_stats=True, streams=None, first_pass_steps=None):
     """One call: partition, integrate on every device, gather.  Returns the Ensemble.Integrate dict."""
     e = Ensemble(chemistry, reactor_type, len(T), devices, partition, chunk)
     e.SetTolerances(rtol, atol); e.SetStopTime(t_end); e.SetMaxNumSteps(max_num_steps); e.SetRetry(retry)
     if configure is not None:
         e.SetConfigure(configure)
+    if streams is not None:
+        e.SetStreams(streams)
+    if first_pass_steps is not None:
+        e.SetFirstPassSteps(first_pass_steps)
     if table is not None:
         e.SetTable(*table)
     return e.Integrate(T, p, Y, want_state=want_state, want_stats=want_stats)

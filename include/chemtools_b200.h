@@ -166,7 +166,7 @@ int ct_batch_set_jacobian_clip(ct_batch*, double thr);
 int ct_batch_set_static_shape(ct_batch*, int on);
 int ct_mech_static_shape(const ct_mech*);
 int ct_batch_set_phase_alignment(ct_batch*, int on); /* 0 off, 1 one group per CTA (default), 2 two groups (even/odd warps) */
-int ct_batch_set_alignment_poll_ns(ct_batch*, int ns); /* sleep between polls of the alignment barrier, default 200 */
+int ct_batch_set_alignment_poll_ns(ct_batch*, int ns); /* 0 (default): waiting warps block in hardware on an mbarrier; > 0: they poll with __nanosleep(ns) */
 int ct_batch_set_alignment_period(ct_batch*, int period); /* meet at every period-th Newton residual; default 1 */
 int ct_batch_set_alignment_max_polls(ct_batch*, int polls); /* bounded wait: give up after that many polls; 0 = unbounded */
 /* scheduling only: keep the N x N Newton matrix out of the per-warp shared-memory slab (shared pool of work slabs for
@@ -247,7 +247,17 @@ int ct_ensemble_set_partition(ct_ensemble*, int mode, int64_t chunk /* reactors 
 int ct_ensemble_set_tolerances(ct_ensemble*, double rtol, double atol);
 int ct_ensemble_set_stop_time(ct_ensemble*, double t_end);
 int ct_ensemble_set_max_steps(ct_ensemble*, int64_t mxstep);
-int ct_ensemble_set_retry(ct_ensemble*, int on);      /* ct_batch_integrate_with_retry per chunk; default on */
+/* recovery pass, once per shard after its last chunk: the ladder of ct_batch_integrate_with_retry over the reactors that
+ * ended with a negative status; default on */
+int ct_ensemble_set_retry(ct_ensemble*, int on);
+/* step budget of the chunk launches when the recovery pass is on (default 10000; 0 = the full budget): a launch lasts as
+ * long as its slowest reactor, so reactors that need more steps are cut off and integrated again from the start with the
+ * full budget (ct_ensemble_set_max_steps) in the shard's one recovery batch, before the ladder (results unaffected) */
+int ct_ensemble_set_first_pass_steps(ct_ensemble*, int64_t steps);
+/* launches in flight per device (host threads + streams per shard, each taking every streams-th chunk): the CTAs of a launch
+ * leave when the work ring is empty, so the next chunk starts on the freed SMs while the slowest reactors of this one
+ * finish; 1..4, default 2 (results unaffected) */
+int ct_ensemble_set_streams(ct_ensemble*, int streams);
 int ct_ensemble_set_hot_first(ct_ensemble*, int on);  /* queue each chunk hottest T0 first; default on (results unaffected) */
 int ct_ensemble_set_configure(ct_ensemble*, ct_batch_configure_fn fn, void* user);
 /* CT_TABLE_TP: common grid t[nt], T[n x nt], p[n x nt]; the arrays are borrowed until ct_ensemble_integrate returns */
@@ -260,8 +270,9 @@ int ct_ensemble_shard_range(const ct_ensemble*, int shard, int64_t* first, int64
  * Returns like ct_batch_integrate: 0 / 1 / the most negative per-reactor code; library errors (<= -100) name the shard */
 int ct_ensemble_integrate(ct_ensemble*, const double* T, const double* p, const double* Y, double* state, double* tau,
                           int32_t* status, int64_t* stats);
-/* per shard after integrate: counts = reactors, chunks, kernel launches, failed before retry, failed after retry;
- * times = sum of k_integrate device ms (CUDA events), wall seconds of the shard's host thread */
+/* per shard after integrate: counts = reactors, chunks, kernel launches, not finished by the chunk launches (negative status,
+ * including those cut off by the first-pass budget), still failed after the recovery pass;
+ * times = sum of k_integrate device ms (CUDA events; launches of one device overlap), wall seconds of the call */
 int ct_ensemble_shard_info(const ct_ensemble*, int shard, int64_t counts[5], double times[2]);
 
 /* ---- stand-alone kernels (parity tests, ncu evidence) ---- */

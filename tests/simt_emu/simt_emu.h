@@ -86,6 +86,7 @@ inline int __any_sync(unsigned, int pred) {
 template <class T> inline T __shfl_down_sync(unsigned, T v, int d) { return emu_xchg(v, emu_lane + d < 32 ? emu_lane + d : emu_lane); }
 
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cmp, unsigned long long val) { unsigned long long e = cmp; __atomic_compare_exchange_n(p, &e, val, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE); return e; }
 inline int atomicCAS(int* p, int cmp, int val) { int e = cmp; __atomic_compare_exchange_n(p, &e, val, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE); return e; }
 inline int atomicExch(int* p, int val) { return __atomic_exchange_n(p, val, __ATOMIC_ACQ_REL); }
 inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }

@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--rtol", type=float, default=1e-8)
     ap.add_argument("--atol", type=float, default=1e-14)
     ap.add_argument("--max-steps", type=int, default=50000)
+    ap.add_argument("--first-pass", type=int, default=-1, help="step budget of the chunk launches (-1 = the library's default)")
+    ap.add_argument("--streams", type=int, default=0)
     ap.add_argument("--out", default="/tmp/config5_map.h5")
     ap.add_argument("--log", default=os.path.join(ROOT, "gpurun_out", "full_map.json"))
     args = ap.parse_args()
@@ -66,6 +68,10 @@ def main():
         T[:] = T_axis[iT]; p[:] = p_axis[ip]; np.take(Y_phi, iphi, axis=0, out=Y)
         e = sharded.Ensemble(chem, ctb.Type.Const_Pres, m, devices, "cyclic", args.chunk)
         e.SetTolerances(args.rtol, args.atol); e.SetStopTime(1e-3); e.SetMaxNumSteps(args.max_steps); e.SetRetry(True)
+        if args.first_pass >= 0:
+            e.SetFirstPassSteps(args.first_pass)
+        if args.streams:
+            e.SetStreams(args.streams)
         out = {k: pin[k].array[:m] for k in ("state", "tau", "status", "stats")}
         t0 = time.perf_counter()
         res = e.Integrate(T, p, Y, out=out)
@@ -84,6 +90,7 @@ def main():
     log.update(integrate_seconds=t_integrate, wall_seconds_incl_ic_generation=wall, reactors_per_s=n_total / t_integrate, reactors_per_minute=60.0 * n_total / t_integrate,
                north_star_target_reactors_per_minute=1.0e6, failed_first=sum(c["failed_first"] for c in log["calls"]), failed_final=int((status < 0).sum()),
                ignited=int(np.isfinite(tau).sum()), nst_mean=float(nst.mean()), nst_max=int(nst.max()),
+               nst_percentiles={str(q): float(np.percentile(nst, q)) for q in (50, 90, 99, 99.9, 99.99)}, first_pass=args.first_pass, streams=args.streams,
                T_end_min=float(T_end.min()), T_end_max=float(T_end.max()), tau_min=float(np.nanmin(tau)), tau_max=float(np.nanmax(tau)))
     # one HDF5 write of the gathered map (the reference's layout: /<group>/<set> f64 + Name / Notation / Unit)
     t0 = time.perf_counter()
