@@ -68,6 +68,7 @@ def lib():
         "ct_h5_create": (vp, []),
         "ct_h5_destroy": (None, [vp]),
         "ct_h5_add_dataset": (i32, [vp, cs, i32, lp, dp, cs, cs, cs]),
+        "ct_h5_set_layout": (i32, [vp, i64, i32, i32]),
         "ct_h5_write": (i32, [vp, cs]),
         "ct_device_count": (i32, []),
         "ct_set_device": (i32, [i32]),

@@ -348,6 +348,11 @@ int ct_h5_add_dataset(ct_h5* h, const char* path, int rank, const int64_t* dims,
   } catch (const std::exception& e) { return fail(CT_ERR_INVALID, e.what()); }
   return 0;
 }
+int ct_h5_set_layout(ct_h5* h, int64_t chunk_elems, int deflate_level, int vlen_strings) {
+  if (!h || chunk_elems < 0) return fail(CT_ERR_INVALID, "bad argument");
+  try { h->f.set_layout((uint64_t)chunk_elems, deflate_level, vlen_strings != 0); } catch (const std::exception& e) { return fail(CT_ERR_INVALID, e.what()); }
+  return 0;
+}
 int ct_h5_write(ct_h5* h, const char* filename) {
   if (!h || !filename) return fail(CT_ERR_INVALID, "null argument");
   try { h->f.write(filename); } catch (const std::exception& e) { return fail(CT_ERR_FILESYSTEM, e.what()); }

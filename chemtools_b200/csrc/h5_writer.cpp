@@ -5,10 +5,14 @@
 // (/<group>/<set>), three string attributes Name / Notation / Unit per dataset.  scripts/results/results.py reads it
 // as f[group][set][:] and .attrs.  libhdf5 is not available in this environment, so the file is produced directly
 // from the HDF5 File Format Specification (version-0 superblock, version-1 object headers, symbol-table groups =
-// v1 B-tree + local heap + SNOD nodes, contiguous little-endian IEEE f64 datasets, fixed-length string attributes),
-// i.e. the oldest, most widely readable structures.  The reference's datasets are 1-D extendible/chunked/deflated
-// because it appends one sample at a time; the batch path knows the final length and writes contiguous datasets of
-// rank 1 (one reactor) or rank 2 ([reactor][sample]).
+// v1 B-tree + local heap + SNOD nodes, little-endian IEEE f64 datasets), i.e. the oldest, most widely readable
+// structures.  String attributes are variable-length strings like the reference's (H5::StrType(0, H5T_VARIABLE),
+// hdf5_writer.cpp:194-208: a class-9 datatype whose value is a {length, global-heap collection, object index} reference
+// into one "GCOL" collection), so that h5py returns `str` and results.py's `attrs['Notation'] + ' ('` works; fixed-length
+// strings stay selectable.  The reference's datasets are 1-D, unlimited, chunked by 1000 and deflated at level 6 because it
+// appends one sample at a time (hdf5_writer.cpp:156-181); the batch path knows the final length and by default writes
+// contiguous datasets of rank 1 (one reactor) or rank 2 ([reactor][sample]); set_layout(1000, 6) reproduces the
+// reference's storage for rank-1 datasets (layout class 2, v1 chunk B-tree, filter pipeline {deflate}, max dim unlimited).
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
@@ -18,6 +22,8 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+
+#include <zlib.h>
 
 #include "h5_writer.hpp"
 
@@ -43,10 +49,11 @@ struct Buf {
 size_t pad8(size_t n) { return (n + 7) & ~size_t(7); }
 
 // ---- header messages (data only, unpadded)
-std::vector<uint8_t> msg_dataspace(const std::vector<uint64_t>& dims) {
+std::vector<uint8_t> msg_dataspace(const std::vector<uint64_t>& dims, bool unlimited = false) {
   Buf m;
-  m.u8(1); m.u8((unsigned)dims.size()); m.u8(0); m.u8(0); m.u32(0);
+  m.u8(1); m.u8((unsigned)dims.size()); m.u8(unlimited ? 1 : 0); m.u8(0); m.u32(0);
   for (uint64_t d : dims) m.u64(d);
+  if (unlimited) for (size_t i = 0; i < dims.size(); ++i) m.u64(UNDEF);  // H5S_UNLIMITED
   return m.b;
 }
 std::vector<uint8_t> msg_datatype_f64() {
@@ -67,9 +74,33 @@ std::vector<uint8_t> msg_datatype_string(size_t len) {
   m.u32((uint32_t)len);
   return m.b;
 }
-std::vector<uint8_t> msg_fill_value() {
+std::vector<uint8_t> msg_datatype_vlen_string() {
   Buf m;
-  m.u8(2); m.u8(2); m.u8(0); m.u8(0);  // version 2, late allocation, write time on allocation, no fill value defined
+  m.u8(0x19);              // version 1, class 9 (variable-length)
+  m.u8(0x01); m.u8(0x00); m.u8(0);  // type = string, null-terminated, ASCII
+  m.u32(16);               // on-disk element: u32 length + u64 collection address + u32 object index
+  const std::vector<uint8_t> base = msg_datatype_string(1);  // base type: one character (H5T_C_S1)
+  m.bytes(base.data(), base.size());
+  return m.b;
+}
+std::vector<uint8_t> msg_fill_value(bool chunked) {
+  Buf m;
+  m.u8(2); m.u8(chunked ? 3 : 2); m.u8(0); m.u8(0);  // version 2, late / incremental allocation, write time on allocation, no fill value defined
+  return m.b;
+}
+std::vector<uint8_t> msg_layout_chunked(uint64_t btree, const std::vector<uint64_t>& chunk_dims) {
+  Buf m;
+  m.u8(3); m.u8(2); m.u8((unsigned)chunk_dims.size() + 1); m.u64(btree);
+  for (uint64_t d : chunk_dims) m.u32((uint32_t)d);
+  m.u32(8);  // dataset element size
+  return m.b;
+}
+std::vector<uint8_t> msg_filter_deflate(int level) {
+  Buf m;
+  m.u8(1); m.u8(1); m.u16(0); m.u32(0);                 // version 1, one filter
+  m.u16(1); m.u16(8); m.u16(0); m.u16(1);               // H5Z_FILTER_DEFLATE, name length, flags, one client value
+  m.bytes("deflate\0", 8);
+  m.u32((uint32_t)level); m.u32(0);                     // client data + padding (odd count)
   return m.b;
 }
 std::vector<uint8_t> msg_layout_contiguous(uint64_t addr, uint64_t size) {
@@ -77,14 +108,17 @@ std::vector<uint8_t> msg_layout_contiguous(uint64_t addr, uint64_t size) {
   m.u8(3); m.u8(1); m.u64(addr); m.u64(size);
   return m.b;
 }
-std::vector<uint8_t> msg_attribute(const std::string& name, const std::string& value) {
-  const std::vector<uint8_t> dt = msg_datatype_string(value.size() + 1), ds = msg_dataspace({});
+// heap = {collection address, object index} of the value in the global heap, or {0, 0} for a fixed-length string
+std::vector<uint8_t> msg_attribute(const std::string& name, const std::string& value, std::pair<uint64_t, uint32_t> heap) {
+  const bool vlen = heap.second != 0;
+  const std::vector<uint8_t> dt = vlen ? msg_datatype_vlen_string() : msg_datatype_string(value.size() + 1), ds = msg_dataspace({});
   Buf m;
   m.u8(1); m.u8(0); m.u16((unsigned)name.size() + 1); m.u16((unsigned)dt.size()); m.u16((unsigned)ds.size());
   m.bytes(name.c_str(), name.size() + 1); m.pad8();
   m.bytes(dt.data(), dt.size()); m.pad8();
   m.bytes(ds.data(), ds.size()); m.pad8();
-  m.bytes(value.c_str(), value.size() + 1);
+  if (vlen) { m.u32((uint32_t)value.size()); m.u64(heap.first); m.u32(heap.second); }
+  else m.bytes(value.c_str(), value.size() + 1);
   return m.b;
 }
 std::vector<uint8_t> msg_symbol_table(uint64_t btree, uint64_t heap) {
@@ -115,6 +149,11 @@ struct Node {
   std::vector<uint64_t> dims;
   std::vector<double> data;
   std::vector<std::pair<std::string, std::string>> attrs;
+  uint64_t chunk = 0;  // > 0: rank-1 dataset stored in chunks of that many elements, unlimited max dim
+  int deflate = 0;
+  std::vector<std::vector<uint8_t>> chunks;    // stored bytes of every chunk (after the filter)
+  std::vector<uint64_t> chunk_addr, cleaf_addr;  // chunk data / chunk B-tree leaf nodes
+  uint64_t croot_addr = 0;
   // layout
   uint64_t header_addr = 0, btree_addr = 0, heap_addr = 0, heap_data_addr = 0, data_addr = 0;
   std::vector<uint64_t> snod_addr;
@@ -125,18 +164,86 @@ struct Node {
 size_t btree_node_size() { return 24 + (2 * K_INTERNAL + 1) * 8 + 2 * K_INTERNAL * 8; }
 size_t snod_size() { return 8 + 2 * K_LEAF * 40; }
 
-std::vector<Msg> dataset_msgs(const Node& n) {
+// global heap of the attribute strings: unique values, one collection (object indices are 16 bits wide)
+struct StringHeap {
+  bool on = true;
+  std::map<std::string, uint32_t> index;
+  std::vector<const std::string*> order;
+  uint64_t addr = 0;
+  void add(const std::string& v) {
+    if (!on || index.count(v)) return;
+    const uint32_t i = (uint32_t)index.size() + 1;
+    if (i > 65535) throw std::runtime_error("too many distinct attribute strings for one global heap collection");
+    order.push_back(&index.emplace(v, i).first->first);
+  }
+  std::pair<uint64_t, uint32_t> ref(const std::string& v) const {
+    if (!on) return {0, 0};
+    return {addr, index.at(v)};
+  }
+  size_t size() const {  // collection size: header + objects + the free-space object, at least 4096 (H5HG_MINSIZE)
+    size_t sz = 16;
+    for (auto* v : order) sz += 16 + pad8(v->size());
+    sz += 16;
+    return std::max<size_t>(4096, (sz + 4095) & ~size_t(4095));
+  }
+  std::vector<uint8_t> bytes() const {
+    const size_t total = size();
+    Buf h;
+    h.bytes("GCOL", 4); h.u8(1); h.u8(0); h.u8(0); h.u8(0); h.u64(total);
+    for (auto* v : order) {
+      h.u16(index.at(*v)); h.u16(1); h.u32(0); h.u64(v->size());
+      h.bytes(v->data(), v->size()); h.pad8();
+    }
+    const size_t rest = total - h.size();  // object 0 = the free space, its size includes its own header
+    h.u16(0); h.u16(0); h.u32(0); h.u64(rest);
+    h.zeros(total - h.size());
+    return h.b;
+  }
+};
+
+const int K_CHUNK = 32;  // chunk B-tree K (the library default; a version-0 superblock cannot say otherwise)
+size_t chunk_key_size() { return 8 + 8 * 2; }  // rank 1: size, filter mask, offset, 0
+size_t chunk_node_size() { return 24 + (2 * K_CHUNK + 1) * chunk_key_size() + 2 * K_CHUNK * 8; }
+
+std::vector<Msg> dataset_msgs(const Node& n, const StringHeap& sh) {
   std::vector<Msg> m;
-  m.push_back({0x0001, msg_dataspace(n.dims)});
+  m.push_back({0x0001, msg_dataspace(n.dims, n.chunk > 0)});
   m.push_back({0x0003, msg_datatype_f64()});
-  m.push_back({0x0005, msg_fill_value()});
-  m.push_back({0x0008, msg_layout_contiguous(n.data_addr, n.data.size() * 8)});
-  for (auto& a : n.attrs) m.push_back({0x000C, msg_attribute(a.first, a.second)});
+  m.push_back({0x0005, msg_fill_value(n.chunk > 0)});
+  if (n.chunk > 0) {
+    if (n.deflate > 0) m.push_back({0x000B, msg_filter_deflate(n.deflate)});
+    m.push_back({0x0008, msg_layout_chunked(n.chunks.empty() ? UNDEF : (n.croot_addr ? n.croot_addr : n.cleaf_addr[0]), {n.chunk})});
+  } else {
+    m.push_back({0x0008, msg_layout_contiguous(n.data_addr, n.data.size() * 8)});
+  }
+  for (auto& a : n.attrs) m.push_back({0x000C, msg_attribute(a.first, a.second, sh.ref(a.second))});
   return m;
 }
 
+// stored form of the chunks of a rank-1 dataset: full chunks (the tail is zero-filled), deflated if asked
+void make_chunks(Node& n) {
+  n.chunks.clear();
+  if (n.chunk == 0) return;
+  const size_t ne = n.data.size();
+  for (size_t c0 = 0; c0 < ne; c0 += n.chunk) {
+    std::vector<double> raw(n.chunk, 0.0);
+    std::copy(n.data.begin() + c0, n.data.begin() + std::min(ne, c0 + (size_t)n.chunk), raw.begin());
+    std::vector<uint8_t> out(raw.size() * 8);
+    std::memcpy(out.data(), raw.data(), out.size());
+    if (n.deflate > 0) {
+      uLongf dl = compressBound((uLong)out.size());
+      std::vector<uint8_t> z(dl);
+      if (compress2(z.data(), &dl, out.data(), (uLong)out.size(), n.deflate) != Z_OK) throw std::runtime_error("deflate failed");
+      z.resize(dl);
+      out.swap(z);
+    }
+    n.chunks.push_back(std::move(out));
+  }
+  if (n.chunks.size() > (size_t)4 * K_CHUNK * K_CHUNK) throw std::runtime_error("too many chunks for a two-level chunk B-tree");
+}
+
 // assign addresses depth first; returns the next free address
-uint64_t layout(Node& n, uint64_t at) {
+uint64_t layout(Node& n, uint64_t at, const StringHeap& sh) {
   at = pad8(at);
   if (n.is_group) {
     n.header_addr = at;
@@ -154,14 +261,23 @@ uint64_t layout(Node& n, uint64_t at) {
     if (nsn > (size_t)2 * K_INTERNAL) throw std::runtime_error("too many entries in one HDF5 group for a single B-tree node");
     n.snod_addr.clear();
     for (size_t i = 0; i < nsn; ++i) { n.snod_addr.push_back(at); at += snod_size(); }
-    for (auto& kv : n.children) at = layout(*kv.second, at);
+    for (auto& kv : n.children) at = layout(*kv.second, at, sh);
   } else {
     n.header_addr = at;
-    n.header_size = object_header(dataset_msgs(n)).size();
+    make_chunks(n);
+    if (n.chunk > 0 && !n.chunks.empty()) { n.cleaf_addr.assign((n.chunks.size() + 2 * K_CHUNK - 1) / (2 * K_CHUNK), 0); n.croot_addr = n.cleaf_addr.size() > 1 ? 1 : 0; }
+    n.header_size = object_header(dataset_msgs(n, sh)).size();  // sizes only: the addresses are assigned below
     at += n.header_size;
     at = pad8(at);
-    n.data_addr = at;
-    at += n.data.size() * 8;
+    if (n.chunk > 0) {
+      for (auto& a : n.cleaf_addr) { a = at; at += chunk_node_size(); }
+      if (n.cleaf_addr.size() > 1) { n.croot_addr = at; at += chunk_node_size(); } else n.croot_addr = 0;
+      n.chunk_addr.clear();
+      for (auto& c : n.chunks) { n.chunk_addr.push_back(at); at = pad8(at + c.size()); }
+    } else {
+      n.data_addr = at;
+      at += n.data.size() * 8;
+    }
   }
   return at;
 }
@@ -171,9 +287,40 @@ void put(std::vector<uint8_t>& file, uint64_t addr, const std::vector<uint8_t>& 
   std::memcpy(file.data() + addr, bytes.data(), bytes.size());
 }
 
-void emit(const Node& n, std::vector<uint8_t>& file) {
+// one node of a rank-1 chunk B-tree (node type 1): keys {stored size, filter mask, element offset, 0} around child pointers
+std::vector<uint8_t> chunk_node(int level, const std::vector<uint64_t>& child, const std::vector<uint32_t>& nbytes, const std::vector<uint64_t>& offset,
+                                uint64_t end_offset, uint64_t left, uint64_t right) {
+  Buf t;
+  t.bytes("TREE", 4); t.u8(1); t.u8((unsigned)level); t.u16((unsigned)child.size()); t.u64(left); t.u64(right);
+  for (size_t i = 0; i < child.size(); ++i) {
+    t.u32(nbytes[i]); t.u32(0); t.u64(offset[i]); t.u64(0);
+    t.u64(child[i]);
+  }
+  t.u32(0); t.u32(0); t.u64(end_offset); t.u64(0);
+  t.zeros(chunk_node_size() - t.size());
+  return t.b;
+}
+
+void emit(const Node& n, std::vector<uint8_t>& file, const StringHeap& sh) {
   if (!n.is_group) {
-    put(file, n.header_addr, object_header(dataset_msgs(n)));
+    put(file, n.header_addr, object_header(dataset_msgs(n, sh)));
+    if (n.chunk > 0) {
+      const size_t per = 2 * K_CHUNK, nc = n.chunks.size();
+      std::vector<uint64_t> root_child, root_off;
+      std::vector<uint32_t> root_nb;
+      for (size_t l = 0; l < n.cleaf_addr.size(); ++l) {
+        const size_t lo = l * per, hi = std::min(nc, lo + per);
+        std::vector<uint64_t> child, off;
+        std::vector<uint32_t> nb;
+        for (size_t c = lo; c < hi; ++c) { child.push_back(n.chunk_addr[c]); off.push_back(c * n.chunk); nb.push_back((uint32_t)n.chunks[c].size()); }
+        put(file, n.cleaf_addr[l], chunk_node(0, child, nb, off, hi * n.chunk, l ? n.cleaf_addr[l - 1] : UNDEF,
+                                              l + 1 < n.cleaf_addr.size() ? n.cleaf_addr[l + 1] : UNDEF));
+        root_child.push_back(n.cleaf_addr[l]); root_off.push_back(lo * n.chunk); root_nb.push_back(nb[0]);
+      }
+      if (n.croot_addr) put(file, n.croot_addr, chunk_node(1, root_child, root_nb, root_off, nc * n.chunk, UNDEF, UNDEF));
+      for (size_t c = 0; c < nc; ++c) put(file, n.chunk_addr[c], n.chunks[c]);
+      return;
+    }
     std::vector<uint8_t> raw(n.data.size() * 8);
     if (!raw.empty()) std::memcpy(raw.data(), n.data.data(), raw.size());  // host is little-endian (x86-64 / aarch64)
     put(file, n.data_addr, raw);
@@ -216,12 +363,17 @@ void emit(const Node& n, std::vector<uint8_t>& file) {
   }
   t.zeros(btree_node_size() - t.size());
   put(file, n.btree_addr, t.b);
-  for (auto& kv : n.children) emit(*kv.second, file);
+  for (auto& kv : n.children) emit(*kv.second, file, sh);
+}
+
+void collect_strings(const Node& n, StringHeap& sh) {
+  for (auto& a : n.attrs) sh.add(a.second);
+  for (auto& kv : n.children) collect_strings(*kv.second, sh);
 }
 
 }  // namespace
 
-struct H5File::Impl { Node root; };
+struct H5File::Impl { Node root; bool vlen_strings = true; uint64_t chunk = 0; int deflate = 0; };
 
 H5File::H5File() : impl_(new Impl) {}
 H5File::~H5File() { delete impl_; }
@@ -248,6 +400,11 @@ static Node* descend(Node& root, const std::string& path, bool create_last_as_gr
   return cur;
 }
 
+void H5File::set_layout(uint64_t chunk_elems, int deflate_level, bool vlen_strings) {
+  if (deflate_level < 0 || deflate_level > 9) throw std::runtime_error("deflate level must be 0..9");
+  impl_->chunk = chunk_elems; impl_->deflate = chunk_elems ? deflate_level : 0; impl_->vlen_strings = vlen_strings;
+}
+
 void H5File::create_group(const std::string& path) { descend(impl_->root, path, true, nullptr); }
 
 void H5File::create_dataset(const std::string& path, const std::vector<uint64_t>& dims, const double* data,
@@ -260,14 +417,22 @@ void H5File::create_dataset(const std::string& path, const std::vector<uint64_t>
   std::unique_ptr<Node> d(new Node);
   d->name = leaf; d->is_group = false; d->dims = dims; d->attrs = attrs;
   d->data.assign(data, data + n);
+  if (dims.size() == 1 && impl_->chunk > 0) { d->chunk = impl_->chunk; d->deflate = impl_->deflate; }  // the reference's storage, rank 1 only
   g->children[leaf] = std::move(d);
 }
 
 void H5File::write(const std::string& filename) {
   Node& root = impl_->root;
-  const uint64_t eof = layout(root, 96);
+  StringHeap sh;
+  sh.on = impl_->vlen_strings;
+  if (sh.on) collect_strings(root, sh);
+  if (sh.order.empty()) sh.on = false;
+  uint64_t at = 96;
+  if (sh.on) { sh.addr = at; at += sh.size(); }
+  const uint64_t eof = layout(root, at, sh);
   std::vector<uint8_t> file((size_t)eof, 0);
-  emit(root, file);
+  if (sh.on) put(file, sh.addr, sh.bytes());
+  emit(root, file, sh);
   Buf sb;
   const uint8_t sig[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
   sb.bytes(sig, 8);

@@ -12,6 +12,11 @@ class HDF5Writer:
     def __init__(self):
         self._h = lib().ct_h5_create()
 
+    def set_layout(self, chunk_elems=0, deflate_level=0, vlen_strings=True):
+        """Storage of the datasets added afterwards: (1000, 6) = the reference's unlimited / chunked / deflated rank-1
+        datasets (hdf5_writer.cpp:156-181); vlen_strings: variable-length string attributes like the reference's."""
+        check(lib().ct_h5_set_layout(self._h, int(chunk_elems), int(deflate_level), int(bool(vlen_strings))))
+
     def add(self, path, data, name=None, notation=None, unit=None):
         a = np.ascontiguousarray(data, dtype=np.float64)
         dims = np.array(a.shape, dtype=np.int64)
@@ -30,9 +35,12 @@ class HDF5Writer:
             pass
 
 
-def write_case_hdf5(filename, res, energy_enabled=True):
-    """One reactor, the reference's layout verbatim (1-D datasets of n_outputs samples)."""
+def write_case_hdf5(filename, res, energy_enabled=True, reference_storage=True):
+    """One reactor, the reference's layout verbatim: 1-D datasets of n_outputs samples, variable-length string attributes
+    and (reference_storage) the reference's unlimited dimension, chunks of 1000 and deflate level 6."""
     w = HDF5Writer()
+    if reference_storage:
+        w.set_layout(1000, 6, True)
     w.add("/Time/Time", res["time"], "Time", "t", "s")
     if energy_enabled:
         w.add("/Temperature/Temperature", res["temperature"], "Temperature", "T", "K")

@@ -100,6 +100,11 @@ ct_h5* ct_h5_create(void);
 void ct_h5_destroy(ct_h5*);
 int ct_h5_add_dataset(ct_h5*, const char* path, int rank, const int64_t* dims, const double* data, const char* name,
                       const char* notation, const char* unit);
+/* storage of the datasets added afterwards: chunk_elems > 0 = rank-1 datasets unlimited, chunked and deflated as the
+ * reference creates them (chunk 1000, level 6: hdf5_writer.cpp:156-181), 0 = contiguous (default).  vlen_strings (file-wide,
+ * default 1): attributes as variable-length strings like the reference's H5::StrType(0, H5T_VARIABLE) (:194-208), so that
+ * h5py hands scripts/results/results.py `str` values; 0 = fixed-length strings */
+int ct_h5_set_layout(ct_h5*, int64_t chunk_elems, int deflate_level, int vlen_strings);
 int ct_h5_write(ct_h5*, const char* filename);
 
 /* ---- device selection / plumbing (no reference counterpart; the reference is single-threaded CPU) */

@@ -1,8 +1,11 @@
 """TEST INFRASTRUCTURE: a minimal structural HDF5 reader (version-0 superblock, v1 object headers, symbol-table
-groups, contiguous datasets, string attributes), written from the HDF5 File Format Specification independently of the
-emitter's code paths: it walks the file the way libhdf5 does (superblock -> root symbol-table entry -> B-tree ->
-SNOD -> object headers).  h5py / libhdf5 are not available offline; this reader is what checks the emitted files."""
+groups, contiguous and chunked / deflated datasets, fixed- and variable-length string attributes with their global heap),
+written from the HDF5 File Format Specification independently of the emitter's code paths: it walks the file the way
+libhdf5 does (superblock -> root symbol-table entry -> B-tree -> SNOD -> object headers -> chunk B-tree / global heap).
+h5py / libhdf5 are not available offline; this reader is what checks the emitted files (tools/verify_h5.py runs the
+reference's own accessors wherever h5py exists)."""
 import struct
+import zlib
 
 import numpy as np
 
@@ -77,10 +80,82 @@ class H5Min:
         return out
 
     @staticmethod
-    def _dataspace(m):
+    def _dataspace(m, want_max=False):
         assert m[0] == 1
         rank, flags = m[1], m[2]
-        return list(struct.unpack_from("<%dQ" % rank, m, 8))
+        assert flags in (0, 1)
+        dims = list(struct.unpack_from("<%dQ" % rank, m, 8))
+        if want_max:
+            return dims, (list(struct.unpack_from("<%dQ" % rank, m, 8 + 8 * rank)) if flags & 1 else None)
+        return dims
+
+    def _global_heap_object(self, addr, index):
+        """Object `index` of the global heap collection at `addr` (walks the collection like H5HG does)."""
+        b = self.b
+        assert b[addr:addr + 4] == b"GCOL" and b[addr + 4] == 1
+        size = struct.unpack_from("<Q", b, addr + 8)[0]
+        assert size >= 4096 and addr + size <= len(b)
+        p, end, found, seen_free = addr + 16, addr + size, None, False
+        while p + 16 <= end:
+            idx, refs, _, osz = struct.unpack_from("<HHIQ", b, p)
+            if idx == 0:  # free space: its size includes its own header and must run to the end of the collection
+                assert p + osz == end
+                seen_free = True
+                break
+            assert refs >= 1
+            if idx == index:
+                found = b[p + 16:p + 16 + osz]
+            p += 16 + ((osz + 7) & ~7)
+        assert seen_free or p == end
+        assert found is not None, "global heap object %d not found" % index
+        return found
+
+    def _chunked(self, lay, dims, pline):
+        """Layout class 2: rank-1 chunks through the v1 chunk B-tree (node type 1)."""
+        b = self.b
+        ndim = lay[2]
+        assert ndim == len(dims) + 1 == 2
+        bt = struct.unpack_from("<Q", lay, 3)[0]
+        cdim, esz = struct.unpack_from("<II", lay, 11)
+        assert esz == 8
+        out = np.zeros(dims[0])
+        if bt == UNDEF:
+            assert dims[0] == 0
+            return out, cdim
+        covered = []
+
+        def walk(node, lo_expect):
+            assert b[node:node + 4] == b"TREE" and b[node + 4] == 1
+            level, used = b[node + 5], struct.unpack_from("<H", b, node + 6)[0]
+            assert 1 <= used <= 64
+            p = node + 24
+            keys, kids = [], []
+            for i in range(used + 1):
+                nbytes, mask, off, zero = struct.unpack_from("<IIQQ", b, p)
+                assert zero == 0 and off % cdim == 0
+                keys.append((nbytes, mask, off)); p += 24
+                if i < used:
+                    kids.append(struct.unpack_from("<Q", b, p)[0]); p += 8
+            assert keys[0][2] == lo_expect and all(keys[i][2] < keys[i + 1][2] for i in range(used))
+            for i in range(used):
+                if level > 0:
+                    walk(kids[i], keys[i][2])
+                else:
+                    nbytes, mask, off = keys[i]
+                    assert mask == 0
+                    raw = b[kids[i]:kids[i] + nbytes]
+                    if pline:
+                        raw = zlib.decompress(raw)
+                    assert len(raw) == 8 * cdim
+                    v = np.frombuffer(raw, dtype="<f8")
+                    n = min(cdim, dims[0] - off)
+                    out[off:off + n] = v[:n]
+                    assert np.all(v[n:] == 0)
+                    covered.append((off, n))
+            return keys[-1][2]
+        walk(bt, 0)
+        assert sum(n for _, n in covered) == dims[0]
+        return out, cdim
 
     @staticmethod
     def _datatype(m):
@@ -92,6 +167,11 @@ class H5Min:
             off, prec, eloc, esz, mloc, msz, bias = struct.unpack_from("<HHBBBBI", m, 8)
             assert (off, prec, eloc, esz, mloc, msz, bias) == (0, 64, 52, 11, 0, 52, 1023) and m[2] == 63
             return ("f64", size)
+        if cls == 9:  # variable-length: string type, null-terminated ASCII, base type = one character
+            assert m[1] & 0xF == 1 and (m[1] >> 4) == 0 and m[2] & 0xF == 0 and size == 16
+            base = m[8:]
+            assert base[0] == 0x13 and struct.unpack_from("<I", base, 4)[0] == 1
+            return ("vstr", size)
         assert cls == 3
         return ("str", size)
 
@@ -102,14 +182,27 @@ class H5Min:
             bt, hp = struct.unpack_from("<QQ", dict(msgs)[0x11], 0)
             return self._group(bt, hp)
         d = dict((t, m) for t, m in msgs if t != 0x0C)
-        dims = self._dataspace(d[0x01])
+        dims, maxdims = self._dataspace(d[0x01], True)
         kind, size = self._datatype(d[0x03])
         lay = d[0x08]
-        assert kind == "f64" and lay[0] == 3 and lay[1] == 1
-        a, nbytes = struct.unpack_from("<QQ", lay, 2)
-        n = int(np.prod(dims)) if dims else 1
-        assert nbytes == 8 * n
-        data = np.frombuffer(self.b, dtype="<f8", count=n, offset=a).reshape(dims)
+        assert kind == "f64" and lay[0] == 3 and lay[1] in (1, 2)
+        storage = {"layout": "contiguous", "maxdims": maxdims}
+        if lay[1] == 1:
+            a, nbytes = struct.unpack_from("<QQ", lay, 2)
+            n = int(np.prod(dims)) if dims else 1
+            assert nbytes == 8 * n and maxdims is None and 0x0B not in d
+            data = np.frombuffer(self.b, dtype="<f8", count=n, offset=a).reshape(dims)
+        else:
+            pline = None
+            if 0x0B in d:  # filter pipeline: exactly {deflate, level}
+                fm = d[0x0B]
+                assert fm[0] == 1 and fm[1] == 1
+                fid, nlen, flags, ncd = struct.unpack_from("<HHHH", fm, 8)
+                assert fid == 1 and nlen % 8 == 0 and ncd == 1 and fm[16:16 + nlen].split(b"\0")[0] == b"deflate"
+                pline = struct.unpack_from("<I", fm, 16 + nlen)[0]
+            assert maxdims == [UNDEF] and d[0x05][1] == 3
+            data, cdim = self._chunked(lay, dims, pline)
+            storage = {"layout": "chunked", "chunk": cdim, "deflate": pline, "maxdims": maxdims}
         attrs = {}
         for t, m in msgs:
             if t != 0x0C:
@@ -120,6 +213,14 @@ class H5Min:
             name = m[p:p + nsz].split(b"\0")[0].decode(); p += (nsz + 7) & ~7
             kind, size = self._datatype(m[p:p + dtsz]); p += (dtsz + 7) & ~7
             assert self._dataspace(m[p:p + dssz]) == []; p += (dssz + 7) & ~7
-            assert kind == "str"
-            attrs[name] = m[p:p + size].split(b"\0")[0].decode()
-        return {"data": data, "attrs": attrs}
+            if kind == "vstr":
+                ln, gaddr, gidx = struct.unpack_from("<IQI", m, p)
+                val = self._global_heap_object(gaddr, gidx)
+                assert len(val) == ln and b"\0" not in val
+                attrs[name] = val.decode()
+                storage.setdefault("attr_kinds", set()).add("vlen")
+            else:
+                assert kind == "str"
+                attrs[name] = m[p:p + size].split(b"\0")[0].decode()
+                storage.setdefault("attr_kinds", set()).add("fixed")
+        return {"data": data, "attrs": attrs, "storage": storage}

@@ -50,3 +50,43 @@ def test_batch_layout_and_many_entries(ctb, tmp_path):
     assert len(h["big"]) == 150 and h["big"]["d149"]["data"][1] == 149.0 and h["scalar"]["x"]["data"] == 3.5
     with pytest.raises(ctb.reactors.CtError):
         w.add("/big/d000", np.zeros(2))      # duplicate object
+
+
+def test_variable_length_string_attributes_and_reference_storage(ctb, tmp_path):
+    """The reference writes Name / Notation / Unit as variable-length strings (H5::StrType(0, H5T_VARIABLE),
+    src/results/hdf5_writer.cpp:194-208) and its datasets unlimited, chunked by 1000 and deflated at level 6 (:156-181).
+    Default here: vlen strings (one global heap collection, values deduplicated); set_layout(1000, 6) = the reference's
+    storage for rank-1 datasets, incl. a two-level chunk B-tree beyond 64 chunks; fixed-length strings stay selectable."""
+    from chemtools_b200.results import HDF5Writer
+    rng = np.random.default_rng(4)
+    short, long_ = rng.random(2500), np.cumsum(rng.random(70001))
+    w = HDF5Writer()
+    w.set_layout(1000, 6, True)
+    w.add("/Time/Time", short, "Time", "t", "s")
+    w.add("/Temperature/Temperature", long_, "Temperature", "T", "K")
+    w.add("/Temperature/Empty", np.zeros(0), "Empty", "e", "-")
+    w.set_layout(0, 0, True)
+    w.add("/Batch/T", rng.random((3, 5)), "Temperature", "T", "K")   # same strings again: one heap object each
+    f = tmp_path / "ref_storage.h5"
+    w.write(str(f))
+    h = H5Min(str(f)).root
+    t = h["Time"]["Time"]
+    assert np.array_equal(t["data"], short) and t["attrs"] == {"Name": "Time", "Notation": "t", "Unit": "s"}
+    assert t["storage"] == {"layout": "chunked", "chunk": 1000, "deflate": 6, "maxdims": [0xFFFFFFFFFFFFFFFF], "attr_kinds": {"vlen"}}
+    T = h["Temperature"]["Temperature"]
+    assert np.array_equal(T["data"], long_) and T["storage"]["layout"] == "chunked"      # 71 chunks: root + two leaves
+    assert h["Temperature"]["Empty"]["data"].shape == (0,)
+    b = h["Batch"]["T"]
+    assert b["storage"]["layout"] == "contiguous" and b["attrs"] == {"Name": "Temperature", "Notation": "T", "Unit": "K"}
+    raw = open(f, "rb").read()
+    assert raw.count(b"GCOL") == 1 and raw.count(b"Temperature\0") >= 1
+    # fixed-length strings on request
+    w2 = HDF5Writer()
+    w2.set_layout(0, 0, False)
+    w2.add("/a/b", np.arange(4.0), "Name of b", "b", "m/s")
+    w2.write(str(tmp_path / "fixed.h5"))
+    g = H5Min(str(tmp_path / "fixed.h5")).root["a"]["b"]
+    assert g["attrs"] == {"Name": "Name of b", "Notation": "b", "Unit": "m/s"} and g["storage"]["attr_kinds"] == {"fixed"}
+    assert b"GCOL" not in open(tmp_path / "fixed.h5", "rb").read()
+    with pytest.raises(ctb.reactors.CtError):
+        HDF5Writer().set_layout(1000, 12, True)
