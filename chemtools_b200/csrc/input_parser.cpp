@@ -176,14 +176,19 @@ class Reader {
 
 // ------------------------------------------------------------------ units (include/input/types.hpp:99-111)
 struct UnitDef { const char* name; int dim; double scale, offset; };  // value_SI = (value + offset) * scale
-enum { DIM_PRESSURE = 1, DIM_TEMPERATURE, DIM_TIME, DIM_CONCENTRATION };
+// A closed table, not the LLNL units library the reference links (units::unit_from_string): the unit strings of the
+// reference's fixtures and documentation plus the common SI-prefixed forms; anything else is "not a valid unit".  Bare "C"
+// and "F" are coulomb and farad there (not temperature scales), so they are known but not convertible to K.
+enum { DIM_OTHER = 0, DIM_PRESSURE = 1, DIM_TEMPERATURE, DIM_TIME, DIM_CONCENTRATION };
 const UnitDef kUnits[] = {
     {"Pa", DIM_PRESSURE, 1.0, 0}, {"Pascal", DIM_PRESSURE, 1.0, 0}, {"pascal", DIM_PRESSURE, 1.0, 0}, {"kPa", DIM_PRESSURE, 1e3, 0},
     {"MPa", DIM_PRESSURE, 1e6, 0}, {"atm", DIM_PRESSURE, 101325.0, 0}, {"bar", DIM_PRESSURE, 1e5, 0}, {"mbar", DIM_PRESSURE, 1e2, 0},
     {"torr", DIM_PRESSURE, 101325.0 / 760.0, 0}, {"Torr", DIM_PRESSURE, 101325.0 / 760.0, 0}, {"psi", DIM_PRESSURE, 6894.757293168, 0},
     {"K", DIM_TEMPERATURE, 1.0, 0}, {"Kelvin", DIM_TEMPERATURE, 1.0, 0}, {"kelvin", DIM_TEMPERATURE, 1.0, 0},
-    {"degC", DIM_TEMPERATURE, 1.0, 273.15}, {"C", DIM_TEMPERATURE, 1.0, 273.15}, {"Celsius", DIM_TEMPERATURE, 1.0, 273.15},
-    {"degF", DIM_TEMPERATURE, 5.0 / 9.0, 459.67}, {"F", DIM_TEMPERATURE, 5.0 / 9.0, 459.67}, {"degR", DIM_TEMPERATURE, 5.0 / 9.0, 0},
+    {"degC", DIM_TEMPERATURE, 1.0, 273.15}, {"Celsius", DIM_TEMPERATURE, 1.0, 273.15},
+    {"degF", DIM_TEMPERATURE, 5.0 / 9.0, 459.67}, {"degR", DIM_TEMPERATURE, 5.0 / 9.0, 0},
+    {"C", DIM_OTHER, 1.0, 0}, {"F", DIM_OTHER, 1.0, 0}, {"m", DIM_OTHER, 1.0, 0}, {"kg", DIM_OTHER, 1.0, 0}, {"J", DIM_OTHER, 1.0, 0}, {"mol", DIM_OTHER, 1.0, 0},
+    {"hPa", DIM_PRESSURE, 1e2, 0}, {"GPa", DIM_PRESSURE, 1e9, 0}, {"mmHg", DIM_PRESSURE, 133.322387415, 0}, {"N/m^2", DIM_PRESSURE, 1.0, 0},
     {"s", DIM_TIME, 1.0, 0}, {"sec", DIM_TIME, 1.0, 0}, {"second", DIM_TIME, 1.0, 0}, {"ms", DIM_TIME, 1e-3, 0}, {"us", DIM_TIME, 1e-6, 0},
     {"ns", DIM_TIME, 1e-9, 0}, {"min", DIM_TIME, 60.0, 0}, {"h", DIM_TIME, 3600.0, 0}, {"hr", DIM_TIME, 3600.0, 0}, {"day", DIM_TIME, 86400.0, 0},
     {"mol/m^3", DIM_CONCENTRATION, 1.0, 0}, {"mol/m3", DIM_CONCENTRATION, 1.0, 0}, {"mmol/L", DIM_CONCENTRATION, 1.0, 0}, {"mol/L", DIM_CONCENTRATION, 1e3, 0},

@@ -13,14 +13,16 @@ UNDEF = 0xFFFFFFFFFFFFFFFF
 
 
 class H5Min:
-    def __init__(self, path):
-        self.b = open(path, "rb").read()
+    def __init__(self, path, userblock=0):
+        """userblock: size of a user block in front of the superblock (file addresses are relative to it)."""
+        whole = open(path, "rb").read()
+        self.b = whole[userblock:]
         b = self.b
         assert b[:8] == b"\x89HDF\r\n\x1a\n", "bad signature"
         assert b[8] == 0 and b[13] == 8 and b[14] == 8, "superblock v0 with 8-byte offsets/lengths expected"
         self.k_leaf, self.k_int = struct.unpack_from("<HH", b, 16)
         base, freesp, eof, drv = struct.unpack_from("<QQQQ", b, 24)
-        assert base == 0 and freesp == UNDEF and drv == UNDEF and eof == len(b), (base, freesp, eof, len(b))
+        assert base == userblock and freesp == UNDEF and drv == UNDEF and eof == len(whole), (base, freesp, eof, len(whole))
         name_off, hdr, cache, _ = struct.unpack_from("<QQII", b, 56)
         assert cache == 1
         self.root = self._object(hdr)

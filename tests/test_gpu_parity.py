@@ -700,3 +700,9 @@ def test_application_yaml_to_hdf5(ctb, chem, omech, tmp_path):
     assert h["Mass fractions"]["H2"]["attrs"] == {"Name": "Y_H2", "Notation": "Y_H2", "Unit": "-"}
     h3 = H5Min(res[2]["file"]).root
     assert sorted(h3) == ["Mass fractions", "Time"]          # Base registers no temperature for the T-fixed types
+    # the reference's storage: unlimited 1-D datasets in chunks of 1000, deflate 6, variable-length string attributes
+    assert h["Temperature"]["Temperature"]["storage"] == {"layout": "chunked", "chunk": 1000, "deflate": 6, "maxdims": [0xFFFFFFFFFFFFFFFF], "attr_kinds": {"vlen"}}
+    # --devices: the batches dealt out over the GPUs of the box give the same files
+    res2 = app.run(str(cfg), n_outputs=100, results_dir=str(tmp_path / "out2"), devices=list(range(min(2, ctb.device_count()))))
+    assert all(np.array_equal(a["mass_fractions"], b["mass_fractions"]) and a["status"] == b["status"] for a, b in zip(res, res2))
+    assert open(res[0]["file"], "rb").read() == open(res2[0]["file"], "rb").read()

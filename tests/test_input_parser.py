@@ -139,3 +139,80 @@ def test_yaml_reader_details(ctb, mech, write):
     p = I.Parser(write(text))
     assert [c.description for c in p.const_V[0].cases] == ["a", "b", "c"]
     assert p.const_V[0].mechanism_description is None and p.const_V[0].description is None
+
+
+# ---- the reference's own fixtures, verbatim (tests/golden/yaml_input/ = /root/reference/tests/data/yaml_input/), and its
+#      test tests/src/input_parser.cpp:23-382 ported assertion by assertion.  Only the mechanism path is rewritten (the
+#      fixtures point at ../data/gri30.cti relative to the reference's build directory).
+GOLDEN_YAML = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "yaml_input")
+
+
+@pytest.fixture()
+def golden(ctb, tmp_path):
+    def g(name):
+        text = open(os.path.join(GOLDEN_YAML, name)).read()
+        assert "../data/gri30.cti" in text or "non_existent_mechanism" in text
+        p = tmp_path / name
+        p.write_text(text.replace("../data/gri30.cti", ctb.mechanism_path("gri30")))
+        return str(p)
+    return g
+
+
+def test_reference_fixtures_error_classes(ctb, golden):
+    """tests/src/input_parser.cpp:27-94: one exception class per malformed file."""
+    from chemtools_b200 import input as I
+    with pytest.raises(I.BadFile):
+        I.Parser("../non_existent_config.yaml")
+    for name, exc in (("config_invalid_node.yaml", I.InvalidNode), ("config_bad_conversion.yaml", I.BadConversion),
+                      ("config_invalid_mech.yaml", I.FilesystemError), ("config_negative_press.yaml", I.InputRuntimeError),
+                      ("config_negative_temp.yaml", I.InputRuntimeError), ("config_duplicate_spec.yaml", I.InputRuntimeError),
+                      ("config_negative_spec.yaml", I.InputRuntimeError), ("config_invalid_spec.yaml", I.InputRuntimeError),
+                      ("config_nonconservative_comp.yaml", I.InputRuntimeError)):
+        with pytest.raises(exc):
+            I.Parser(golden(name))
+        assert exc is I.InputRuntimeError or not issubclass(exc, I.InputRuntimeError)
+
+
+def test_reference_fixture_multiple_reactors(ctb, golden):
+    """tests/src/input_parser.cpp:97-141."""
+    from chemtools_b200 import input as I
+    p = I.Parser(golden("config_multiple_reactors.yaml")).GetParameters()
+    assert len(p.const_P) == 2 and len(p.const_P[0].Cases()) == 3 and len(p.const_P[1].Cases()) == 2
+    assert len(p.const_V) == 1 and len(p.const_V[0].Cases()) == 2
+    assert len(p.const_TP) == 1 and len(p.const_TP[0].Cases()) == 1
+    assert len(p.const_TV) == 1 and len(p.const_TV[0].Cases()) == 2
+
+
+def test_reference_fixture_config_values(ctb, golden):
+    """tests/src/input_parser.cpp:143-382: config.yaml, exact equality as in the reference's REQUIREs."""
+    from chemtools_b200 import input as I
+    p = I.Parser(golden("config.yaml")).GetParameters()
+    assert p.const_P and not p.const_V and not p.const_TP and not p.const_TV
+    assert len(p.const_P) == 1
+    cases = p.const_P[0].Cases()
+    assert len(cases) == 4
+    c = cases[0]
+    assert c.pressure == 101325.0 and c.temperature == 1300.0 and c.time == 1.0e-3
+    assert c.composition_type == "MoleFraction" and c.pairs == [("CH4", 0.1), ("O2", 0.5), ("N2", 0.4)]
+    assert sum(v for _, v in c.pairs) == 1.0
+    c = cases[1]
+    assert c.pressure == 202650.0 and c.temperature == 1298.15 and c.time == 60.0
+    assert c.composition_type == "Concentration" and c.pairs == [("CH4", 0.1), ("O2", 0.5), ("N2", 0.35), ("H2", 0.05)]
+    c = cases[2]
+    assert c.pressure == 150000.0 and c.temperature == 1368.15 and c.time == 3600.0
+    assert c.composition_type == "Concentration" and c.pairs == [("CH3", 0.03), ("CH4", 0.07), ("O2", 0.5), ("N2", 0.4)]
+    c = cases[3]
+    assert c.pressure == 201326.0 and c.temperature == 1250.0 and c.time == 1.0
+    assert c.composition_type == "MassFraction" and c.pairs == [("CH4", 0.15), ("O2", 0.45), ("N2", 0.4)]
+    assert sum(v for _, v in c.pairs) == 1.0
+    assert p.const_P[0].description == "case set 1" and p.const_P[0].mechanism_description == "Constant pressure reactor - mechanism 1"
+    assert [k.description for k in cases] == ["useful case 1.%d" % i for i in range(1, 5)]
+
+
+def test_units_follow_the_llnl_units_library(ctb, mech, write):
+    """Bare "C" and "F" are coulomb and farad in the units library the reference uses, not temperature scales: the
+    reference rejects them as not convertible to K (std::invalid_argument)."""
+    from chemtools_b200 import input as I
+    for u in ("C", "F"):
+        with pytest.raises(I.InvalidUnit):
+            I.Parser(write(case_set("CONSTANT_PRESSURE", mech, [case(tu=u)])))

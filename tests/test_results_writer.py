@@ -90,3 +90,51 @@ def test_variable_length_string_attributes_and_reference_storage(ctb, tmp_path):
     assert b"GCOL" not in open(tmp_path / "fixed.h5", "rb").read()
     with pytest.raises(ctb.reactors.CtError):
         HDF5Writer().set_layout(1000, 12, True)
+
+
+LIBHDF5_FILE = None
+try:
+    import scipy.io.matlab.tests as _smt
+    import os as _os
+    LIBHDF5_FILE = _os.path.join(_os.path.dirname(_smt.__file__), "data", "testhdf5_7.4_GLNX86.mat")
+    if not _os.path.exists(LIBHDF5_FILE):
+        LIBHDF5_FILE = None
+except Exception:
+    pass
+
+
+@pytest.mark.skipif(LIBHDF5_FILE is None, reason="scipy's MATLAB v7.3 test file (written by the real HDF5 library) not found")
+def test_structures_against_a_file_written_by_libhdf5(ctb, tmp_path):
+    """The only file in the image that the real HDF5 library wrote (a MATLAB v7.3 file = HDF5 behind a 512-byte user
+    block): the structural reader walks its superblock, root symbol table, B-tree, SNOD, local heap and object header, and
+    the f64 datatype / dataspace / string-attribute messages the emitter produces are byte-identical in form to
+    libhdf5's own."""
+    import struct
+    from chemtools_b200.results import HDF5Writer
+
+    class Raw(H5Min):
+        def _object(self, addr):
+            msgs = self._messages(addr)
+            if 0x11 in [t for t, _ in msgs]:
+                return self._group(*struct.unpack_from("<QQ", dict(msgs)[0x11], 0))
+            return msgs
+    real = Raw(LIBHDF5_FILE, 512).root
+    assert list(real) == ["testdouble"]
+    rm = real["testdouble"]
+    rd = dict((t, m) for t, m in rm if t != 0x0C)
+    assert H5Min._datatype(rd[0x03]) == ("f64", 8) and H5Min._dataspace(rd[0x01]) == [9, 1]
+    w = HDF5Writer()
+    w.set_layout(0, 0, False)
+    w.add("/testdouble", np.zeros((9, 1)), "double")
+    f = tmp_path / "mine.h5"
+    w.write(str(f))
+    mine = Raw(str(f)).root["testdouble"]
+    md = dict((t, m) for t, m in mine if t != 0x0C)
+    assert md[0x03] == rd[0x03][:len(md[0x03])]          # IEEE f64 little-endian datatype message: identical bytes
+    assert md[0x01] == rd[0x01][:len(md[0x01])]          # dataspace message: identical bytes
+    ra = [m for t, m in rm if t == 0x0C][0]
+    ma = [m for t, m in mine if t == 0x0C][0]
+    # attribute message: version, name / datatype / dataspace sizes, fixed-length null-terminated ASCII string type, scalar space
+    assert ra[:2] == ma[:2] and struct.unpack_from("<HH", ra, 4) == struct.unpack_from("<HH", ma, 4) == (8, 8)
+    assert ra[8:21] == b"MATLAB_class\0" and ra[24:28] == ma[16:20] == bytes([0x13, 0, 0, 0])
+    assert ra[32:40] == ma[24:32]                        # scalar dataspace
