@@ -78,6 +78,7 @@ inline T emu_xchg(T v, int src) {
 }
 template <class T> inline T __shfl_sync(unsigned, T v, int src) { return emu_xchg(v, src); }
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_xchg(v, emu_lane ^ m); }
+inline long long __double_as_longlong(double x) { long long r; std::memcpy(&r, &x, 8); return r; }
 inline int __any_sync(unsigned, int pred) {
   int v = pred ? 1 : 0;
   for (int o = 16; o > 0; o >>= 1) v |= emu_xchg(v, emu_lane ^ o);
