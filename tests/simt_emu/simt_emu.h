@@ -84,6 +84,7 @@ inline int __any_sync(unsigned, int pred) {
   for (int o = 16; o > 0; o >>= 1) v |= emu_xchg(v, emu_lane ^ o);
   return v;
 }
+template <class T> inline T __shfl_up_sync(unsigned, T v, int d) { return emu_xchg(v, emu_lane - d >= 0 ? emu_lane - d : emu_lane); }
 template <class T> inline T __shfl_down_sync(unsigned, T v, int d) { return emu_xchg(v, emu_lane + d < 32 ? emu_lane + d : emu_lane); }
 
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
