@@ -582,7 +582,7 @@ int ct_batch_set_stop_time(ct_batch* b, double t_end) {
 int ct_batch_set_max_steps(ct_batch* b, int64_t mx) {
   if (!b) return fail(CT_ERR_INVALID, "null batch");
   if (mx < 0) return fail(CT_ILL_INPUT, "SetMaxNumSteps: maximum number of steps must be non-negative");
-  b->mxstep = mx > 0 ? mx : 500;
+  b->mxstep = mx > 0 ? std::min<int64_t>(mx, 2147483647LL) : 500;  // the device counts steps in 32 bits
   return 0;
 }
 int ct_batch_set_max_order(ct_batch* b, int q) {
