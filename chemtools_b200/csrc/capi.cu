@@ -819,12 +819,125 @@ int ct_batch_integrate(ct_batch* b, double t_target) {
   return out;
 }
 
-// Integrate to the stop time, then re-run the reactors that ended with a negative CVODE status as a small batch under
-// other Jacobian / Newton options and merge what succeeded (the recovery IStrategy::Integrate only sketches,
-// interface.cpp:462-473).  About 0.05 % of stiff CH4 ensembles crawl into CV_TOO_MUCH_WORK / CV_ERR_FAILURE: a property of
-// the clipped right-hand side shared with the reference's algorithm, chaotic in which reactor it hits, so a
-// second attempt under different arithmetic almost always gets through.  Ladder: Jacobian clip 1, then LU instead of
-// the inverse, then difference-quotient Jacobian + LU (the reference's own configuration).
+}  // extern "C" (the ladder below is internal)
+
+namespace {
+
+// Recovery ladder over the reactors `bad` of batch b (indices into b): they are re-run from their initial conditions under
+// other Jacobian / Newton options (Jacobian clip 1; LU instead of the inverse; difference-quotient Jacobian + LU, the
+// reference's own configuration) and each takes the result of the FIRST rung, in that order, that brings it to the stop
+// time.  About 0.05-0.2 % of stiff CH4 ensembles crawl into CV_TOO_MUCH_WORK / CV_ERR_FAILURE: a property of the clipped
+// right-hand side shared with the reference's algorithm, chaotic in which reactor it hits, so another attempt
+// under different arithmetic almost always gets through.  While three times the set fits one wave of warps the three
+// rungs run CONCURRENTLY (three small batches, three streams, three host threads): the pass costs its slowest rung instead
+// of their sum; larger sets go rung by rung, each rung only over what the previous one left.  On return `bad` holds the
+// reactors no rung could finish.
+int retry_ladder(ct_batch* b, std::vector<int>& bad) {
+  if (bad.empty()) return 0;
+  if (b->t_start != 0.0) return fail(CT_ERR_UNSUPPORTED, "IntegrateWithRetry after ReInitialise is not supported");
+  struct Alt { double clip; int linsol, jac; };
+  const Alt ladder[3] = {{1.0, LINSOL_INVERSE, CT_JAC_ANALYTIC}, {b->jac_clip, LINSOL_LU, CT_JAC_ANALYTIC}, {b->jac_clip, LINSOL_LU, CT_JAC_DQ}};
+  const int K = b->K, N = b->N;
+  int dev = 0;
+  CT_CUDA(cudaGetDevice(&dev));
+  DeviceInfo di;
+  if (int r = device_info(di)) return r;
+  const int thr = 256;
+  auto blocks = [&](int64_t work) { return (int)std::max<int64_t>(1, std::min<int64_t>((work + thr - 1) / thr, 2048)); };
+  int rung = 0;
+  while (rung < 3 && !bad.empty()) {
+    const int m = (int)bad.size();
+    const int nconc = ((int64_t)(3 - rung) * m <= (int64_t)di.sms * 12) ? 3 - rung : 1;  // rungs run at once
+    // initial conditions of the set, gathered once on the device and shared by the concurrent rungs
+    DevBuf<int> idx;
+    DevBuf<double> gT, gp, gY, gtT, gtp;
+    CT_CUDA(idx.alloc(m)); CT_CUDA(gT.alloc(m)); CT_CUDA(gp.alloc(m)); CT_CUDA(gY.alloc((size_t)m * K));
+    CT_CUDA(cudaMemcpyAsync(idx.p, bad.data(), m * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+    k_gather_rows<double><<<blocks(m), thr, 0, b->stream>>>(b->pT0, idx.p, m, 1, gT.p);
+    k_gather_rows<double><<<blocks(m), thr, 0, b->stream>>>(b->pp0, idx.p, m, 1, gp.p);
+    k_gather_rows<double><<<blocks((int64_t)m * K), thr, 0, b->stream>>>(b->pY0, idx.p, m, K, gY.p);
+    if (b->rt == CT_TABLE_TP) {
+      CT_CUDA(gtT.alloc((size_t)m * b->nt)); CT_CUDA(gtp.alloc((size_t)m * b->nt));
+      k_gather_rows<double><<<blocks((int64_t)m * b->nt), thr, 0, b->stream>>>(b->tab_T.p, idx.p, m, b->nt, gtT.p);
+      k_gather_rows<double><<<blocks((int64_t)m * b->nt), thr, 0, b->stream>>>(b->tab_p.p, idx.p, m, b->nt, gtp.p);
+    }
+    CT_CUDA(cudaGetLastError());
+    CT_CUDA(cudaStreamSynchronize(b->stream));
+    b->aux_launches += 3;
+    struct Run { std::unique_ptr<ct_batch> r; cudaStream_t s = nullptr; int rc = 0; std::string err; std::vector<int> st; };
+    std::vector<Run> runs(nconc);
+    for (int c = 0; c < nconc; ++c) {
+      int stc = 0;
+      runs[c].r.reset(ct_batch_create(b->mech, b->rt, m, &stc));
+      if (!runs[c].r) return stc;
+      ct_batch* r = runs[c].r.get();
+      if (nconc > 1) { CT_CUDA(cudaStreamCreateWithFlags(&runs[c].s, cudaStreamNonBlocking)); r->stream = runs[c].s; } else r->stream = b->stream;
+      r->rtol = b->rtol; r->atol = b->atol; r->t_stop = b->t_stop; r->mxstep = b->mxstep; r->opts = b->opts;
+      r->max_order = b->max_order; r->ign_mode = b->ign_mode; r->ign_value = b->ign_value; r->use_static_shape = b->use_static_shape;
+      r->jac_clip = ladder[rung + c].clip; r->linsol = ladder[rung + c].linsol; r->jac_mode = ladder[rung + c].jac;
+      if (b->atol_is_vec) {
+        CT_CUDA(r->atol_vec.alloc(N));
+        CT_CUDA(cudaMemcpy(r->atol_vec.p, b->atol_vec.p, N * sizeof(double), cudaMemcpyDeviceToDevice));
+        r->atol_is_vec = true;
+      }
+      if (b->rt == CT_TABLE_TP) {  // the table views are borrowed from the gathered copies
+        CT_CUDA(r->tab_t.alloc(b->nt));
+        CT_CUDA(cudaMemcpy(r->tab_t.p, b->tab_t.p, b->nt * sizeof(double), cudaMemcpyDeviceToDevice));
+        CT_CUDA(r->tab_T.alloc((size_t)m * b->nt)); CT_CUDA(r->tab_p.alloc((size_t)m * b->nt));
+        CT_CUDA(cudaMemcpy(r->tab_T.p, gtT.p, (size_t)m * b->nt * sizeof(double), cudaMemcpyDeviceToDevice));
+        CT_CUDA(cudaMemcpy(r->tab_p.p, gtp.p, (size_t)m * b->nt * sizeof(double), cudaMemcpyDeviceToDevice));
+        r->nt = b->nt;
+      }
+    }
+    auto one = [&](int c) {
+      Run& R = runs[c];
+      if (cudaSetDevice(dev) != cudaSuccess) { R.rc = CT_ERR_CUDA; R.err = "cudaSetDevice"; return; }
+      int rc = ct_batch_set_ic_device(R.r.get(), gT.p, gp.p, gY.p);
+      if (rc >= 0) rc = ct_batch_integrate(R.r.get(), b->t_stop);
+      if (rc <= CT_ERR_INVALID) { R.rc = rc; R.err = g_err; return; }
+      R.st.resize(m);
+      if (cudaMemcpyAsync(R.st.data(), R.r->status.p, m * sizeof(int), cudaMemcpyDeviceToHost, R.r->stream) != cudaSuccess ||
+          cudaStreamSynchronize(R.r->stream) != cudaSuccess) { R.rc = CT_ERR_CUDA; R.err = "status copy"; }
+    };
+    if (nconc > 1) {
+      std::vector<std::thread> th;
+      for (int c = 0; c < nconc; ++c) th.emplace_back(one, c);
+      for (auto& t : th) t.join();
+    } else one(0);
+    for (int c = 0; c < nconc; ++c) if (runs[c].rc < 0) { for (auto& R : runs) if (R.s) cudaStreamDestroy(R.s); return fail(runs[c].rc, runs[c].err); }
+    // every reactor takes the first rung that got through: masks on the host, merges on the device
+    std::vector<int> taken(m, 0), still;
+    DevBuf<int> ok;
+    CT_CUDA(ok.alloc(m));
+    for (int c = 0; c < nconc; ++c) {
+      ct_batch* r = runs[c].r.get();
+      std::vector<int> mask(m, -1);
+      for (int jx = 0; jx < m; ++jx) if (!taken[jx] && runs[c].st[jx] >= 0) { mask[jx] = 0; taken[jx] = 1; }
+      CT_CUDA(cudaMemcpyAsync(ok.p, mask.data(), m * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+      k_scatter_rows<double><<<blocks((int64_t)m * N), thr, 0, b->stream>>>(r->state.p, idx.p, ok.p, m, N, b->state.p);
+      k_scatter_rows<double><<<blocks(m), thr, 0, b->stream>>>(r->tau.p, idx.p, ok.p, m, 1, b->tau.p);
+      k_scatter_rows<double><<<blocks(m), thr, 0, b->stream>>>(r->tcur.p, idx.p, ok.p, m, 1, b->tcur.p);
+      k_scatter_rows<long long><<<blocks((int64_t)m * 8), thr, 0, b->stream>>>(r->stats.p, idx.p, ok.p, m, 8, b->stats.p);
+      k_scatter_rows<double><<<blocks((int64_t)m * 6), thr, 0, b->stream>>>(r->stats_ex.p, idx.p, ok.p, m, 6, b->stats_ex.p);
+      k_scatter_rows<int><<<blocks(m), thr, 0, b->stream>>>(r->status.p, idx.p, ok.p, m, 1, b->status.p);
+      CT_CUDA(cudaGetLastError());
+      CT_CUDA(cudaStreamSynchronize(b->stream));  // `mask` goes out of scope
+      b->launches += r->launches; b->aux_launches += r->aux_launches + 6;
+    }
+    for (auto& R : runs) if (R.s) cudaStreamDestroy(R.s);
+    for (int jx = 0; jx < m; ++jx) if (!taken[jx]) still.push_back(bad[jx]);
+    bad.swap(still);
+    rung += nconc;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Integrate to the stop time, then the recovery ladder over the reactors that ended with a negative CVODE status (what
+// IStrategy::Integrate only sketches, interface.cpp:462-473).  Fresh batches only.
 int ct_batch_integrate_with_retry(ct_batch* b, int64_t* n_failed_first, int64_t* n_failed_final) {
   if (!b) return fail(CT_ERR_INVALID, "null batch");
   if (!b->fresh) return fail(CT_ILL_INPUT, "IntegrateWithRetry needs a fresh batch (set the initial conditions again)");
@@ -835,65 +948,7 @@ int ct_batch_integrate_with_retry(ct_batch* b, int64_t* n_failed_first, int64_t*
   std::vector<int> bad;
   for (int64_t i = 0; i < b->n; ++i) if (st[i] < 0) bad.push_back((int)i);
   if (n_failed_first) *n_failed_first = (int64_t)bad.size();
-  struct Alt { double clip; int linsol, jac; };
-  const Alt ladder[3] = {{1.0, LINSOL_INVERSE, CT_JAC_ANALYTIC}, {b->jac_clip, LINSOL_LU, CT_JAC_ANALYTIC}, {b->jac_clip, LINSOL_LU, CT_JAC_DQ}};
-  const int K = b->K, N = b->N;
-  for (int step = 0; step < 3 && !bad.empty(); ++step) {
-    const int m = (int)bad.size();
-    int stc = 0;
-    ct_batch* r = ct_batch_create(b->mech, b->rt, m, &stc);
-    if (!r) return stc;
-    std::unique_ptr<ct_batch> guard(r);
-    r->stream = b->stream; r->rtol = b->rtol; r->atol = b->atol; r->t_stop = b->t_stop; r->mxstep = b->mxstep; r->opts = b->opts;
-    r->max_order = b->max_order; r->ign_mode = b->ign_mode; r->ign_value = b->ign_value; r->use_static_shape = b->use_static_shape;
-    r->jac_clip = ladder[step].clip; r->linsol = ladder[step].linsol; r->jac_mode = ladder[step].jac;
-    if (b->atol_is_vec) {
-      CT_CUDA(r->atol_vec.alloc(N));
-      CT_CUDA(cudaMemcpyAsync(r->atol_vec.p, b->atol_vec.p, N * sizeof(double), cudaMemcpyDeviceToDevice, b->stream));
-      r->atol_is_vec = true;
-    }
-    DevBuf<int> idx, ok;
-    CT_CUDA(idx.alloc(m)); CT_CUDA(ok.alloc(m));
-    CT_CUDA(cudaMemcpyAsync(idx.p, bad.data(), m * sizeof(int), cudaMemcpyHostToDevice, b->stream));
-    CT_CUDA(r->T0.alloc(m)); CT_CUDA(r->p0.alloc(m)); CT_CUDA(r->Y0.alloc((size_t)m * K));
-    const int thr = 256;
-    auto blocks = [&](int64_t work) { return (int)std::max<int64_t>(1, std::min<int64_t>((work + thr - 1) / thr, 2048)); };
-    k_gather_rows<double><<<blocks(m), thr, 0, b->stream>>>(b->pT0, idx.p, m, 1, r->T0.p);
-    k_gather_rows<double><<<blocks(m), thr, 0, b->stream>>>(b->pp0, idx.p, m, 1, r->p0.p);
-    k_gather_rows<double><<<blocks((int64_t)m * K), thr, 0, b->stream>>>(b->pY0, idx.p, m, K, r->Y0.p);
-    CT_CUDA(cudaGetLastError());
-    r->pT0 = r->T0.p; r->pp0 = r->p0.p; r->pY0 = r->Y0.p;
-    if (int e = finish_ic(r)) return e;
-    if (b->rt == CT_TABLE_TP) {
-      CT_CUDA(r->tab_t.alloc(b->nt)); CT_CUDA(r->tab_T.alloc((size_t)m * b->nt)); CT_CUDA(r->tab_p.alloc((size_t)m * b->nt));
-      CT_CUDA(cudaMemcpyAsync(r->tab_t.p, b->tab_t.p, b->nt * sizeof(double), cudaMemcpyDeviceToDevice, b->stream));
-      k_gather_rows<double><<<blocks((int64_t)m * b->nt), thr, 0, b->stream>>>(b->tab_T.p, idx.p, m, b->nt, r->tab_T.p);
-      k_gather_rows<double><<<blocks((int64_t)m * b->nt), thr, 0, b->stream>>>(b->tab_p.p, idx.p, m, b->nt, r->tab_p.p);
-      CT_CUDA(cudaGetLastError());
-      r->nt = b->nt;
-    }
-    if (b->t_start != 0.0) {  // ReInitialise'd batch: restart the retried reactors from the same state and time
-      return fail(CT_ERR_UNSUPPORTED, "IntegrateWithRetry after ReInitialise is not supported");
-    }
-    const int rr = ct_batch_integrate(r, b->t_stop);
-    if (rr <= CT_ERR_INVALID) return rr;
-    b->launches += r->launches; b->aux_launches += r->aux_launches + 3;
-    // merge the reactors that got through (ok[r] = their new status >= 0)
-    CT_CUDA(cudaMemcpyAsync(ok.p, r->status.p, m * sizeof(int), cudaMemcpyDeviceToDevice, b->stream));
-    k_scatter_rows<double><<<blocks((int64_t)m * N), thr, 0, b->stream>>>(r->state.p, idx.p, ok.p, m, N, b->state.p);
-    k_scatter_rows<double><<<blocks(m), thr, 0, b->stream>>>(r->tau.p, idx.p, ok.p, m, 1, b->tau.p);
-    k_scatter_rows<double><<<blocks(m), thr, 0, b->stream>>>(r->tcur.p, idx.p, ok.p, m, 1, b->tcur.p);
-    k_scatter_rows<long long><<<blocks((int64_t)m * 8), thr, 0, b->stream>>>(r->stats.p, idx.p, ok.p, m, 8, b->stats.p);
-    k_scatter_rows<double><<<blocks((int64_t)m * 6), thr, 0, b->stream>>>(r->stats_ex.p, idx.p, ok.p, m, 6, b->stats_ex.p);
-    k_scatter_rows<int><<<blocks(m), thr, 0, b->stream>>>(r->status.p, idx.p, ok.p, m, 1, b->status.p);
-    CT_CUDA(cudaGetLastError());
-    std::vector<int> rs(m);
-    CT_CUDA(cudaMemcpyAsync(rs.data(), r->status.p, m * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
-    CT_CUDA(cudaStreamSynchronize(b->stream));
-    std::vector<int> still;
-    for (int j = 0; j < m; ++j) if (rs[j] < 0) still.push_back(bad[j]);
-    bad.swap(still);
-  }
+  if (int e = retry_ladder(b, bad)) return e;
   if (n_failed_final) *n_failed_final = (int64_t)bad.size();
   int out = 0;
   if (int e = summarize_status(b, &out)) return e;

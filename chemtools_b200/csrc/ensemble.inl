@@ -186,70 +186,75 @@ int run_worker(ct_ensemble* e, int g, int w, int stride, const double* T, const 
   return 0;
 }
 
-// recovery pass of one shard, once, after all its chunks: the reactors that ended with a negative CVODE status are re-run
-// as one small batch, first with the full step budget (if the chunk launches had a smaller one), then under the ladder of
-// ct_batch_integrate_with_retry (Jacobian clip 1; LU instead of the inverse; difference-quotient Jacobian + LU), and the
-// successful ones overwrite their rows.  Same options, same ladder, same per-reactor arithmetic: identical to
-// ct_batch_integrate_with_retry on a single batch with the full budget.
+// recovery pass of one shard, once, after all its chunks: the reactors that ended with a negative CVODE status form one
+// small batch; first the caller's own options with the full step budget (if the chunk launches had a smaller one), then
+// the library's recovery ladder (retry_ladder in capi.cu: Jacobian clip 1; LU instead of the inverse; difference-quotient
+// Jacobian + LU); the successful ones overwrite their rows.  Same options, same ladder, same per-reactor arithmetic:
+// identical to ct_batch_integrate_with_retry on a single batch with the full budget.
 int run_ladder(ct_ensemble* e, int g, const double* T, const double* p, const double* Y, double* state, double* tau, int32_t* status,
                int64_t* stats) {
   ct_ensemble::Shard& S = e->shards[g];
-  std::vector<int64_t> bad = S.bad;
-  std::sort(bad.begin(), bad.end());
-  if (bad.empty()) { S.failed_final = 0; return 0; }
+  std::vector<int64_t> gidx = S.bad;
+  std::sort(gidx.begin(), gidx.end());
+  if (gidx.empty()) { S.failed_final = 0; return 0; }
   CT_CUDA(cudaSetDevice(e->devices[g]));
   cudaStream_t stream = nullptr;
   CT_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sg{stream};
   const int K = e->K, N = e->N, nt = e->nt;
-  // rung 0: the caller's own options with the full step budget (only when the chunk launches ran with a smaller one)
-  for (int rung = (e->first_pass_budget() < e->mxstep) ? 0 : 1; rung < 4 && !bad.empty(); ++rung) {
-    const int64_t m = (int64_t)bad.size();
-    int stc = 0;
-    std::unique_ptr<ct_batch> r(ct_batch_create(e->mech, e->rt, m, &stc));
-    if (!r) return stc;
-    if (int rc = configure_batch(e, r.get(), stream, false)) return rc;
-    if (rung == 1) r->jac_clip = 1.0;
-    if (rung >= 2) r->linsol = LINSOL_LU;
-    if (rung == 3) r->jac_mode = CT_JAC_DQ;
-    std::vector<double> hT(m), hp(m), hY((size_t)m * K), hTabT, hTabp;
-    if (nt) { hTabT.resize((size_t)m * nt); hTabp.resize((size_t)m * nt); }
-    for (int64_t j = 0; j < m; ++j) {
-      const int64_t i = bad[j];
-      hT[j] = T[i]; hp[j] = p[i];
-      std::memcpy(hY.data() + j * K, Y + i * K, (size_t)K * 8);
-      if (nt) {
-        std::memcpy(hTabT.data() + j * nt, e->tab_T + i * nt, (size_t)nt * 8);
-        std::memcpy(hTabp.data() + j * nt, e->tab_p + i * nt, (size_t)nt * 8);
-      }
+  const int64_t m = (int64_t)gidx.size();
+  int stc = 0;
+  std::unique_ptr<ct_batch> r(ct_batch_create(e->mech, e->rt, m, &stc));
+  if (!r) return stc;
+  if (int rc = configure_batch(e, r.get(), stream, false)) return rc;
+  std::vector<double> hT(m), hp(m), hY((size_t)m * K), hTabT, hTabp;
+  if (nt) { hTabT.resize((size_t)m * nt); hTabp.resize((size_t)m * nt); }
+  for (int64_t j = 0; j < m; ++j) {
+    const int64_t i = gidx[j];
+    hT[j] = T[i]; hp[j] = p[i];
+    std::memcpy(hY.data() + j * K, Y + i * K, (size_t)K * 8);
+    if (nt) {
+      std::memcpy(hTabT.data() + j * nt, e->tab_T + i * nt, (size_t)nt * 8);
+      std::memcpy(hTabp.data() + j * nt, e->tab_p + i * nt, (size_t)nt * 8);
     }
-    if (int rc = ct_batch_set_ic(r.get(), hT.data(), hp.data(), hY.data())) return rc;
-    if (nt) { if (int rc = ct_batch_set_tp_table(r.get(), nt, e->tab_t, hTabT.data(), hTabp.data())) return rc; }
+  }
+  if (int rc = ct_batch_set_ic(r.get(), hT.data(), hp.data(), hY.data())) return rc;
+  if (nt) { if (int rc = ct_batch_set_tp_table(r.get(), nt, e->tab_t, hTabT.data(), hTabp.data())) return rc; }
+  std::vector<int> bad;
+  std::vector<int32_t> oStatus(m);
+  if (e->first_pass_budget() < e->mxstep) {
     const int rc = ct_batch_integrate(r.get(), e->t_stop);
     if (rc <= CT_ERR_INVALID) return rc;
-    S.launches += r->launches + r->aux_launches;
-    std::vector<double> oState((size_t)m * N), oTau(m);
-    std::vector<int32_t> oStatus(m);
-    std::vector<int64_t> oStats((size_t)m * 8);
-    CT_CUDA(cudaMemcpyAsync(oState.data(), r->state.p, (size_t)m * N * 8, cudaMemcpyDeviceToHost, stream));
-    CT_CUDA(cudaMemcpyAsync(oTau.data(), r->tau.p, (size_t)m * 8, cudaMemcpyDeviceToHost, stream));
-    CT_CUDA(cudaMemcpyAsync(oStats.data(), r->stats.p, (size_t)m * 64, cudaMemcpyDeviceToHost, stream));
     CT_CUDA(cudaMemcpyAsync(oStatus.data(), r->status.p, (size_t)m * 4, cudaMemcpyDeviceToHost, stream));
     CT_CUDA(cudaStreamSynchronize(stream));
-    std::vector<int64_t> still;
-    for (int64_t j = 0; j < m; ++j) {
-      if (oStatus[j] < 0) { still.push_back(bad[j]); continue; }
-      const int64_t i = bad[j];
-      if (state) std::memcpy(state + i * N, oState.data() + j * N, (size_t)N * 8);
-      if (tau) tau[i] = oTau[j];
-      if (status) status[i] = oStatus[j];
-      if (stats) std::memcpy(stats + i * 8, oStats.data() + j * 8, 64);
-      if (oStatus[j] != CT_TSTOP_RETURN) S.all_tstop = false;
-    }
-    bad.swap(still);
+    for (int64_t j = 0; j < m; ++j) if (oStatus[j] < 0) bad.push_back((int)j);
+  } else {  // the chunk launches already had the full budget: straight to the ladder
+    if (int rc = precheck_integrate(r.get())) return rc;
+    CT_CUDA(cudaMemsetAsync(r->status.p, 0xFF, (size_t)m * 4, stream));
+    r->launches += 1;  // results will be read from this batch
+    for (int64_t j = 0; j < m; ++j) bad.push_back((int)j);
   }
-  S.failed_final = (int64_t)bad.size();
-  if (bad.empty()) S.worst = 0;
+  if (int rc = retry_ladder(r.get(), bad)) return rc;
+  S.launches += r->launches + r->aux_launches;
+  std::vector<double> oState((size_t)m * N), oTau(m);
+  std::vector<int64_t> oStats((size_t)m * 8);
+  CT_CUDA(cudaMemcpyAsync(oState.data(), r->state.p, (size_t)m * N * 8, cudaMemcpyDeviceToHost, stream));
+  CT_CUDA(cudaMemcpyAsync(oTau.data(), r->tau.p, (size_t)m * 8, cudaMemcpyDeviceToHost, stream));
+  CT_CUDA(cudaMemcpyAsync(oStats.data(), r->stats.p, (size_t)m * 64, cudaMemcpyDeviceToHost, stream));
+  CT_CUDA(cudaMemcpyAsync(oStatus.data(), r->status.p, (size_t)m * 4, cudaMemcpyDeviceToHost, stream));
+  CT_CUDA(cudaStreamSynchronize(stream));
+  int64_t left = 0;
+  for (int64_t j = 0; j < m; ++j) {
+    if (oStatus[j] < 0) { ++left; continue; }
+    const int64_t i = gidx[j];
+    if (state) std::memcpy(state + i * N, oState.data() + j * N, (size_t)N * 8);
+    if (tau) tau[i] = oTau[j];
+    if (status) status[i] = oStatus[j];
+    if (stats) std::memcpy(stats + i * 8, oStats.data() + j * 8, 64);
+    if (oStatus[j] != CT_TSTOP_RETURN) S.all_tstop = false;
+  }
+  S.failed_final = left;
+  if (left == 0) S.worst = 0;
   return 0;
 }
 
