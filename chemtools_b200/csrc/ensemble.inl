@@ -8,8 +8,9 @@
 // Each shard is processed in chunks of `chunk` reactors so that the reactor-indexed scratch of the time-sliced work ring
 // stays below its 4 GiB bound and device memory use does not depend on the ensemble size.
 //
-// Built on the public batch ABI only (ct_batch_create / set_ic / integrate / get_*): a shard is nothing but a sequence of
-// ordinary batches, which is why a sharded run is bit-identical to a single-GPU run of the same reactors.
+// A shard is nothing but a sequence of ordinary batches (ct_batch_create / set_ic / integrate, results read from the batch's
+// device arrays) followed by the library's own recovery ladder (retry_ladder in capi.cu), which is why a sharded run is
+// bit-identical to a single-GPU run of the same reactors.
 
 struct ct_ensemble {
   ct_mech* mech = nullptr;
@@ -47,11 +48,11 @@ struct ct_ensemble {
     if (partition == CT_PARTITION_CYCLIC) return (n - g + G - 1) / G;
     return (n * (g + 1) + G - 1) / G - (n * g + G - 1) / G;
   }
-  // global index of the j-th reactor of shard g
-  // step budget of the chunk launches: a launch lasts as long as its slowest reactor (one warp, ~75 us per step), so the
+  // step budget of the chunk launches: a launch lasts as long as its slowest reactor (one warp, 40-60 us per step), so the
   // few reactors that need more than `first_pass` steps are cut off there and integrated again, with the full budget, in
   // one batch per shard after its last chunk (one long tail per shard instead of one per chunk)
   int64_t first_pass_budget() const { return (retry && first_pass > 0) ? std::min(first_pass, mxstep) : mxstep; }
+  // global index of the j-th reactor of shard g
   int64_t global_index(int g, int64_t j) const {
     const int64_t G = (int64_t)devices.size();
     if (partition == CT_PARTITION_CYCLIC) return g + j * G;
