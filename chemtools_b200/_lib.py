@@ -109,6 +109,7 @@ def lib():
         "ct_batch_set_alignment_poll_ns": (i32, [vp, i32]),
         "ct_batch_set_alignment_max_polls": (i32, [vp, i32]),
         "ct_batch_set_tp_table": (i32, [vp, i32, dp, dp, dp]),
+        "ct_batch_set_v_table": (i32, [vp, i32, dp, dp, dp]),
         "ct_batch_set_order": (i32, [vp, ip]),
         "ct_batch_integrate": (i32, [vp, dbl]),
         "ct_batch_integrate_with_retry": (i32, [vp, lp, lp]),

@@ -497,7 +497,7 @@ int ct_mech_mole_to_mass(const ct_mech* m, int64_t n, const double* X, double* Y
 }
 int ct_mech_flop_model(const ct_mech* m, int reactor_type, double out[4]) {
   if (!m || !out) return fail(CT_ERR_INVALID, "null argument");
-  const int N = reactor_type <= CT_CONST_VOL ? m->C.K + 1 : m->C.K;
+  const int N = rt_has_energy(reactor_type) ? m->C.K + 1 : m->C.K;
   out[0] = m->C.flops_rhs; out[1] = m->C.flops_jac;
   out[2] = 2.0 / 3.0 * (double)N * N * N; out[3] = 2.0 * (double)N * N;
   return 0;
@@ -508,10 +508,10 @@ int ct_set_device(int ordinal) { if (int r = require_device()) return r; CT_CUDA
 
 ct_batch* ct_batch_create(ct_mech* m, int rt, int64_t n, int* status) {
   auto set = [&](int s) { if (status) *status = s; };
-  if (!m || n < 0 || rt < 0 || rt > CT_TABLE_TP) { set(fail(CT_ERR_INVALID, "bad batch arguments")); return nullptr; }
+  if (!m || n < 0 || rt < 0 || rt > CT_TABLE_V) { set(fail(CT_ERR_INVALID, "bad batch arguments")); return nullptr; }
   if (int r = require_device()) { set(r); return nullptr; }
   ct_batch* b = new ct_batch;
-  b->mech = m; b->rt = rt; b->n = n; b->K = m->C.K; b->N = rt <= CT_CONST_VOL ? m->C.K + 1 : m->C.K;
+  b->mech = m; b->rt = rt; b->n = n; b->K = m->C.K; b->N = rt_has_energy(rt) ? m->C.K + 1 : m->C.K;
   set(0);
   return b;
 }
@@ -760,9 +760,21 @@ int ct_batch_set_ignition(ct_batch* b, int mode, double value) {
   b->ign_mode = mode; b->ign_value = value;
   return 0;
 }
+static int set_table(ct_batch* b, int nt, const double* t, const double* T, const double* p);
 int ct_batch_set_tp_table(ct_batch* b, int nt, const double* t, const double* T, const double* p) {
   if (!b || nt < 2 || !t || !T || !p) return fail(CT_ERR_INVALID, "bad table arguments");
   if (b->rt != CT_TABLE_TP) return fail(CT_ERR_INVALID, "T-p table on a reactor type other than CT_TABLE_TP");
+  return set_table(b, nt, t, T, p);
+}
+// prescribed volume and its time derivative (the reference's plan, README.md:18-20): V[n x nt] > 0 in any unit (only
+// V(t) / V(t[0]) enters), dVdt[n x nt] in that unit per second; both interpolated linearly on the common grid
+int ct_batch_set_v_table(ct_batch* b, int nt, const double* t, const double* V, const double* dVdt) {
+  if (!b || nt < 2 || !t || !V || !dVdt) return fail(CT_ERR_INVALID, "bad table arguments");
+  if (b->rt != CT_TABLE_V) return fail(CT_ERR_INVALID, "volume table on a reactor type other than CT_TABLE_V");
+  for (int64_t i = 0; i < b->n * (int64_t)nt; ++i) if (!(V[i] > 0.0)) return fail(CT_ILL_INPUT, "volumes must be positive");
+  return set_table(b, nt, t, V, dVdt);
+}
+static int set_table(ct_batch* b, int nt, const double* t, const double* T, const double* p) {
   for (int i = 1; i < nt; ++i) if (!(t[i] > t[i - 1])) return fail(CT_ILL_INPUT, "table times must increase strictly");
   CT_CUDA(b->tab_t.alloc(nt)); CT_CUDA(b->tab_T.alloc((size_t)b->n * nt)); CT_CUDA(b->tab_p.alloc((size_t)b->n * nt));
   CT_CUDA(cudaMemcpyAsync(b->tab_t.p, t, nt * sizeof(double), cudaMemcpyHostToDevice, b->stream));
@@ -794,7 +806,7 @@ int ct_batch_set_order(ct_batch* b, const int32_t* order) {
 static int precheck_integrate(ct_batch* b) {
   if (!b) return fail(CT_ERR_INVALID, "null batch");
   if (!b->have_ic) return fail(CT_ILL_INPUT, "initial conditions not set");
-  if (b->rt == CT_TABLE_TP && b->nt < 2) return fail(CT_ILL_INPUT, "CT_TABLE_TP reactor without a T-p table");
+  if (rt_has_table(b->rt) && b->nt < 2) return fail(CT_ILL_INPUT, "table reactor (CT_TABLE_TP / CT_TABLE_V) without its table");
   return ensure_runtime_buffers(b);
 }
 
@@ -856,7 +868,7 @@ int retry_ladder(ct_batch* b, std::vector<int>& bad) {
     k_gather_rows<double><<<blocks(m), thr, 0, b->stream>>>(b->pT0, idx.p, m, 1, gT.p);
     k_gather_rows<double><<<blocks(m), thr, 0, b->stream>>>(b->pp0, idx.p, m, 1, gp.p);
     k_gather_rows<double><<<blocks((int64_t)m * K), thr, 0, b->stream>>>(b->pY0, idx.p, m, K, gY.p);
-    if (b->rt == CT_TABLE_TP) {
+    if (rt_has_table(b->rt)) {
       CT_CUDA(gtT.alloc((size_t)m * b->nt)); CT_CUDA(gtp.alloc((size_t)m * b->nt));
       k_gather_rows<double><<<blocks((int64_t)m * b->nt), thr, 0, b->stream>>>(b->tab_T.p, idx.p, m, b->nt, gtT.p);
       k_gather_rows<double><<<blocks((int64_t)m * b->nt), thr, 0, b->stream>>>(b->tab_p.p, idx.p, m, b->nt, gtp.p);
@@ -880,7 +892,7 @@ int retry_ladder(ct_batch* b, std::vector<int>& bad) {
         CT_CUDA(cudaMemcpy(r->atol_vec.p, b->atol_vec.p, N * sizeof(double), cudaMemcpyDeviceToDevice));
         r->atol_is_vec = true;
       }
-      if (b->rt == CT_TABLE_TP) {  // the table views are borrowed from the gathered copies
+      if (rt_has_table(b->rt)) {  // copies of the gathered tables
         CT_CUDA(r->tab_t.alloc(b->nt));
         CT_CUDA(cudaMemcpy(r->tab_t.p, b->tab_t.p, b->nt * sizeof(double), cudaMemcpyDeviceToDevice));
         CT_CUDA(r->tab_T.alloc((size_t)m * b->nt)); CT_CUDA(r->tab_p.alloc((size_t)m * b->nt));

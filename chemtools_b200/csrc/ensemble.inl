@@ -62,6 +62,11 @@ struct ct_ensemble {
 
 namespace {
 
+// T-p table or V-dV/dt table, whichever the reactor type takes
+int batch_set_table(ct_batch* b, int nt, const double* t, const double* A, const double* B) {
+  return b->rt == CT_TABLE_V ? ct_batch_set_v_table(b, nt, t, A, B) : ct_batch_set_tp_table(b, nt, t, A, B);
+}
+
 struct PinnedBuf {
   void* p = nullptr;
   ~PinnedBuf() { if (p) cudaFreeHost(p); }
@@ -140,7 +145,7 @@ int run_worker(ct_ensemble* e, int g, int w, int stride, const double* T, const 
     }
     const int64_t launches_before = batch->launches + batch->aux_launches;
     if (int r = ct_batch_set_ic(batch.get(), cT, cp, cY)) return r;
-    if (nt) { if (int r = ct_batch_set_tp_table(batch.get(), nt, e->tab_t, cTabT, cTabp)) return r; }
+    if (nt) { if (int r = batch_set_table(batch.get(), nt, e->tab_t, cTabT, cTabp)) return r; }
     if (e->hot_first && m > 1) {
       // expected-cost order: hottest first, so that the longest integrations start first (shortens the tail of the queue)
       order.resize(m);
@@ -220,7 +225,7 @@ int run_ladder(ct_ensemble* e, int g, const double* T, const double* p, const do
     }
   }
   if (int rc = ct_batch_set_ic(r.get(), hT.data(), hp.data(), hY.data())) return rc;
-  if (nt) { if (int rc = ct_batch_set_tp_table(r.get(), nt, e->tab_t, hTabT.data(), hTabp.data())) return rc; }
+  if (nt) { if (int rc = batch_set_table(r.get(), nt, e->tab_t, hTabT.data(), hTabp.data())) return rc; }
   std::vector<int> bad;
   std::vector<int32_t> oStatus(m);
   if (e->first_pass_budget() < e->mxstep) {
@@ -276,7 +281,7 @@ int ct_host_free(void* p) {
 
 ct_ensemble* ct_ensemble_create(ct_mech* m, int rt, int64_t n, int n_devices, const int* devices, int* status) {
   auto set = [&](int s) { if (status) *status = s; };
-  if (!m || n < 0 || rt < 0 || rt > CT_TABLE_TP || n_devices < 0) { set(fail(CT_ERR_INVALID, "bad ensemble arguments")); return nullptr; }
+  if (!m || n < 0 || rt < 0 || rt > CT_TABLE_V || n_devices < 0) { set(fail(CT_ERR_INVALID, "bad ensemble arguments")); return nullptr; }
   if (int r = require_device()) { set(r); return nullptr; }
   const int have = ct_device_count();
   std::vector<int> devs;
@@ -287,7 +292,7 @@ ct_ensemble* ct_ensemble_create(ct_mech* m, int rt, int64_t n, int n_devices, co
     for (size_t j = 0; j < i; ++j) if (devs[j] == devs[i]) { set(fail(CT_ERR_INVALID, "a device is listed twice")); return nullptr; }
   }
   ct_ensemble* e = new ct_ensemble;
-  e->mech = m; e->rt = rt; e->n = n; e->K = m->C.K; e->N = rt <= CT_CONST_VOL ? m->C.K + 1 : m->C.K;
+  e->mech = m; e->rt = rt; e->n = n; e->K = m->C.K; e->N = rt_has_energy(rt) ? m->C.K + 1 : m->C.K;
   e->devices = devs;
   e->shards.resize(devs.size());
   set(0);
@@ -341,7 +346,7 @@ int ct_ensemble_set_configure(ct_ensemble* e, ct_batch_configure_fn fn, void* us
 }
 int ct_ensemble_set_tp_table(ct_ensemble* e, int nt, const double* t, const double* T, const double* p) {
   if (!e) return fail(CT_ERR_INVALID, "null ensemble");
-  if (e->rt != CT_TABLE_TP) return fail(CT_ILL_INPUT, "T-p tables belong to CT_TABLE_TP reactors");
+  if (!rt_has_table(e->rt)) return fail(CT_ILL_INPUT, "tables belong to CT_TABLE_TP (T, p) and CT_TABLE_V (V, dV/dt) reactors");
   if (nt < 2 || !t || !T || !p) return fail(CT_ERR_INVALID, "bad table arguments");
   e->nt = nt; e->tab_t = t; e->tab_T = T; e->tab_p = p;
   return 0;
@@ -364,7 +369,7 @@ int ct_ensemble_shard_range(const ct_ensemble* e, int shard, int64_t* first, int
 int ct_ensemble_integrate(ct_ensemble* e, const double* T, const double* p, const double* Y, double* state, double* tau,
                           int32_t* status, int64_t* stats) {
   if (!e || !T || !p || !Y) return fail(CT_ERR_INVALID, "null argument");
-  if (e->rt == CT_TABLE_TP && e->nt < 2) return fail(CT_ILL_INPUT, "CT_TABLE_TP ensemble without a T-p table");
+  if (rt_has_table(e->rt) && e->nt < 2) return fail(CT_ILL_INPUT, "table ensemble (CT_TABLE_TP / CT_TABLE_V) without its table");
   const int G = (int)e->devices.size();
   if (G == 0) return fail(CT_ERR_NO_DEVICE, "no device in the ensemble");
   int prev = 0;

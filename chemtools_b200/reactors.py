@@ -31,6 +31,12 @@ class Type(enum.IntEnum):
     Const_Temp_Pres = 2
     Const_Temp_Vol = 3
     Table_Temp_Pres = 4  # prescribed T(t), p(t) (planned by the reference, README.md:18-20)
+    Table_Vol = 5        # adiabatic, prescribed volume V(t) and dV/dt (planned on the same lines); state [T, Y]
+
+
+def has_energy(reactor_type):
+    """State [T, Y...] (EnergyEnabled reactors) or [Y...]."""
+    return int(reactor_type) in (Type.Const_Pres, Type.Const_Vol, Type.Table_Vol)
 
 
 def _f64(a):
@@ -286,9 +292,18 @@ class ReactorBatch:
         check(lib().ct_batch_set_tp_table(self._h, t.shape[0], _p(t), _p(T), _p(p)))
         self._table = (t, T, p)
 
+    def SetVolumeTable(self, t, V, dVdt):
+        """Prescribed volume and its time derivative (Type.Table_Vol): t[nt], V[n, nt] > 0 in any unit, dVdt[n, nt]."""
+        t = _f64(t); V = _f64(np.atleast_2d(V)); dVdt = _f64(np.atleast_2d(dVdt))
+        if V.shape != (self.n, t.shape[0]) or dVdt.shape != V.shape:
+            raise ValueError("table shapes must be [n, nt]")
+        check(lib().ct_batch_set_v_table(self._h, t.shape[0], _p(t), _p(V), _p(dVdt)))
+        self._table = (t, V, dVdt)
+
     def SetTableFromFunction(self, function, n_points=101, module_path=None):
-        """Prescribed T(t), p(t) from a FunctionP1R2-style Python callable (include/embedded_python/functions.hpp:10-41
-        of the reference: one parameter in, two values out).  `function` is a callable f(t) -> (T, p), or a function
+        """Prescribed T(t), p(t) — or, for Type.Table_Vol, V(t), dV/dt(t) — from a FunctionP1R2-style Python callable
+        (include/embedded_python/functions.hpp:10-41 of the reference: one parameter in, two values out; README.md:18-20
+        names exactly these two uses).  `function` is a callable f(t) -> (T, p), or a function
         name to load from the module file `module_path` like FunctionP1R2::Load(module_path, function_name).  The
         callable is sampled ONCE on the host at n_points equidistant times in [0, t_end] into the device table (linear
         interpolation in the kernel); T and p may be scalars (all reactors) or arrays of length n."""
@@ -303,9 +318,12 @@ class ReactorBatch:
         for k, tk in enumerate(t):
             val = function(float(tk))
             if len(val) != 2:
-                raise ValueError("the profile function must return two values (T, p)")
+                raise ValueError("the profile function must return two values (T, p) or (V, dV/dt)")
             T[:, k] = val[0]; p[:, k] = val[1]
-        self.SetTable(t, T, p)
+        if self.type == Type.Table_Vol:
+            self.SetVolumeTable(t, T, p)
+        else:
+            self.SetTable(t, T, p)
 
     def SetOrder(self, order):
         o = np.ascontiguousarray(order, dtype=np.int32)
@@ -352,13 +370,13 @@ class ReactorBatch:
     State = Solution
 
     def Temperature(self):
-        if self.type > Type.Const_Vol:
+        if not has_energy(self.type):
             raise ValueError("temperature is not a state of this reactor type")
         return self.Solution()[:, 0]
 
     def MassFractions(self):
         s = self.Solution()
-        return s[:, 1:] if self.type <= Type.Const_Vol else s
+        return s[:, 1:] if has_energy(self.type) else s
 
     def Time(self):
         out = np.zeros(self.n)

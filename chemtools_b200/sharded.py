@@ -14,7 +14,7 @@ import ctypes as C
 import numpy as np
 
 from ._lib import CtError, check, dp, ip, lib, lp
-from .reactors import Type
+from .reactors import Type, has_energy
 
 PARTITION = {"block": 0, "cyclic": 1}
 CONFIGURE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
@@ -67,7 +67,7 @@ class Ensemble:
     def __init__(self, chemistry, reactor_type, n, devices=None, partition="block", chunk=0):
         self.chem, self.rt, self.n = chemistry, int(reactor_type), int(n)
         self.K = chemistry.n_species
-        self.N = self.K + 1 if self.rt <= Type.Const_Vol else self.K
+        self.N = self.K + 1 if has_energy(self.rt) else self.K
         st = C.c_int(0)
         if devices is None:
             nd, dv = 0, None
@@ -201,7 +201,7 @@ def write_hdf5(path, chemistry, reactor_type, res, T0=None, p0=None, extra=None)
     output time: /Temperature/Temperature, /Mass fractions/<species>, /Ignition delay/Ignition delay, /Solver/Status,
     /Solver/nst, /Initial conditions/{Temperature, Pressure}; `extra` = {"/group/set": (array, notation, unit)}."""
     from .results import HDF5Writer
-    energy = int(reactor_type) <= Type.Const_Vol
+    energy = has_energy(reactor_type)
     w = HDF5Writer()
     if T0 is not None:
         w.add("/Initial conditions/Temperature", T0, "Initial temperature", "T0", "K")

@@ -16,6 +16,7 @@ except ImportError:  # loaded as a plain file (bench.py --impl reference: numpy 
         Const_Temp_Pres = 2
         Const_Temp_Vol = 3
         Table_Temp_Pres = 4
+        Table_Vol = 5
 
 ONE_ATM = 101325.0
 

@@ -25,7 +25,9 @@ typedef struct ct_batch ct_batch; /* N x { Apps::Reactor::Base + SUNDIALS::CVODE
 
 /* Apps::Reactor::Type (include/applications/reactors/base.hpp:21-27); 4 = prescribed T(t),p(t) table reactor
  * (BASELINE config 4; the reference only plans it, README.md:18-20). */
-enum { CT_CONST_PRES = 0, CT_CONST_VOL = 1, CT_CONST_TEMP_PRES = 2, CT_CONST_TEMP_VOL = 3, CT_TABLE_TP = 4 };
+enum { CT_CONST_PRES = 0, CT_CONST_VOL = 1, CT_CONST_TEMP_PRES = 2, CT_CONST_TEMP_VOL = 3, CT_TABLE_TP = 4,
+       /* adiabatic closed reactor in a prescribed volume V(t), dV/dt (planned next to it, README.md:18-20); state [T, Y] */
+       CT_TABLE_V = 5 };
 
 /* return / status codes. 0, 1 and the negative CV_* values are CVODE's own, which the reference returns
  * unchanged from IStrategy::Integrate (src/sundials/cvode/interface.cpp:454-475). */
@@ -196,6 +198,10 @@ int ct_batch_get_timeline(ct_batch*, int64_t* out /* n x 3 */);
 int ct_batch_set_ignition(ct_batch*, int mode, double value);
 /* prescribed T(t), p(t): common time grid t[nt], per-reactor values T[n x nt], p[n x nt] (CT_TABLE_TP only) */
 int ct_batch_set_tp_table(ct_batch*, int nt, const double* t, const double* T, const double* p);
+/* prescribed volume and its time derivative (CT_TABLE_V only): common grid t[nt], V[n x nt] > 0 in any unit (only
+ * V(t) / V(t[0]) enters: rho = rho0 V(t0) / V(t)), dVdt[n x nt] in that unit per second; the energy equation is
+ * ConstVol::EnergyDerivative (reactors.cpp:96-109) plus the boundary work -p dV/dt / (V rho cv) */
+int ct_batch_set_v_table(ct_batch*, int nt, const double* t, const double* V, const double* dVdt);
 /* optional processing order of the work queue (a permutation of 0..n-1), e.g. most expensive first */
 int ct_batch_set_order(ct_batch*, const int32_t* order);
 
@@ -265,7 +271,8 @@ int ct_ensemble_set_first_pass_steps(ct_ensemble*, int64_t steps);
 int ct_ensemble_set_streams(ct_ensemble*, int streams);
 int ct_ensemble_set_hot_first(ct_ensemble*, int on);  /* queue each chunk hottest T0 first; default on (results unaffected) */
 int ct_ensemble_set_configure(ct_ensemble*, ct_batch_configure_fn fn, void* user);
-/* CT_TABLE_TP: common grid t[nt], T[n x nt], p[n x nt]; the arrays are borrowed until ct_ensemble_integrate returns */
+/* CT_TABLE_TP: common grid t[nt], T[n x nt], p[n x nt] (CT_TABLE_V: V[n x nt], dVdt[n x nt] in their place); the arrays are
+ * borrowed until ct_ensemble_integrate returns */
 int ct_ensemble_set_tp_table(ct_ensemble*, int nt, const double* t, const double* T, const double* p);
 /* global reactor indices of a shard: first, first + stride, ... (count of them).  ct_partition_range is the same rule
  * without a handle (host arithmetic only: callers that run one process per GPU use it to pick their slice) */

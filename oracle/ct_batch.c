@@ -34,7 +34,7 @@ static void run_one(batch_job* J, long i) {
   const omech* m = J->m;
   const int K = om_nspecies(m);
   oreactor* r = or_create(m, J->type, J->T0[i], J->p0[i], J->Y0 + i * K);
-  if (J->type == OR_TABLE_TP) or_set_table(r, J->nt, J->tab_t, J->tab_T + i * J->nt, J->tab_p + i * J->nt);
+  if (J->type == OR_TABLE_TP || J->type == OR_TABLE_V) or_set_table(r, J->nt, J->tab_t, J->tab_T + i * J->nt, J->tab_p + i * J->nt);
   const int N = or_nstate(r);
   const int n_out = J->n_out;
   double* y = (double*)malloc(N * 8);
@@ -50,7 +50,7 @@ static void run_one(batch_job* J, long i) {
     cvo_set_solver_options(c, (int)o[4], (int)o[5], (int)o[6], o[3]);
     if (o[7] > 0) cvo_set_max_order(c, (int)o[7]);
   }
-  if (J->type <= OR_CONST_VOL) cvo_watch(c, 0, J->ign_mode == 0 ? J->ign_value : J->T0[i] + J->ign_value);
+  if (J->type <= OR_CONST_VOL || J->type == OR_TABLE_V) cvo_watch(c, 0, J->ign_mode == 0 ? J->ign_value : J->T0[i] + J->ign_value);
   int status = 0;
   double tret = 0.0;
   if (n_out > 0) {

@@ -97,6 +97,7 @@ struct oreactor {
   double T0, p0;
   double* Y0;
   double rho, p, T; /* current thermo state */
+  double rho_init;  /* density of the initial state (OR_TABLE_V: rho(t) = rho_init V(t0) / V(t)) */
   double mmw;
   /* work */
   double *ym, *conc, *cp_R, *h_RT, *s_R, *grt, *wdot, *qf, *qr, *rkc, *energy;
@@ -242,6 +243,7 @@ oreactor* or_create(const omech* m, int type, double T, double p, const double* 
   /* constructors: ConstVol/ConstTempVol fix rho from (T0,p0,Y0) (reactors.cpp:83-85,:175-180);
      ConstPres/ConstTempPres keep p (reactors.cpp:35-42,:133-141). */
   set_state_TPY(r, T, p, Y);
+  r->rho_init = r->rho;
   return r;
 }
 void or_set_table(oreactor* r, int nt, const double* t, const double* T, const double* p) {
@@ -254,10 +256,11 @@ void or_destroy(oreactor* r) {
   free(r->grt); free(r->wdot); free(r->energy); free(r->qf); free(r->qr); free(r->rkc);
   free(r->tab_t); free(r->tab_T); free(r->tab_p); free(r);
 }
-int or_nstate(const oreactor* r) { return (r->type <= OR_CONST_VOL) ? r->m->K + 1 : r->m->K; }
+static int has_energy(int type) { return type <= OR_CONST_VOL || type == OR_TABLE_V; }
+int or_nstate(const oreactor* r) { return has_energy(r->type) ? r->m->K + 1 : r->m->K; }
 void or_initial_state(const oreactor* r, double* y) {
   int K = r->m->K;
-  if (r->type <= OR_CONST_VOL) { y[0] = r->T0; memcpy(y + 1, r->Y0, K * 8); }
+  if (has_energy(r->type)) { y[0] = r->T0; memcpy(y + 1, r->Y0, K * 8); }
   else memcpy(y, r->Y0, K * 8);
 }
 double or_density(const oreactor* r) { return r->rho; }
@@ -267,6 +270,7 @@ int or_rhs(oreactor* r, double t, const double* y, double* ydot) {
   const omech* m = r->m;
   const int K = m->K;
   double* dY;
+  double vdv = 0.0; /* OR_TABLE_V: (dV/dt) / V */
   switch (r->type) {
     case OR_CONST_PRES: set_state_TPY(r, y[0], r->p0, y + 1); dY = ydot + 1; break;
     case OR_CONST_VOL: {
@@ -277,6 +281,16 @@ int or_rhs(oreactor* r, double t, const double* y, double* ydot) {
     case OR_CONST_TEMP_PRES: set_state_TPY(r, r->T0, r->p0, y); dY = ydot; break;
     case OR_CONST_TEMP_VOL: { double rho0 = r->rho; set_state_TRY(r, r->T0, rho0, y); dY = ydot; break; }
     case OR_TABLE_TP: { double T, p; table_lookup(r, t, &T, &p); set_state_TPY(r, T, p, y); dY = ydot; break; }
+    case OR_TABLE_V: {
+      /* closed system of fixed mass in the prescribed volume: rho = rho_init V(t0) / V(t) */
+      double V, Vd;
+      table_lookup(r, t, &V, &Vd);
+      const double V0 = r->nt > 0 ? r->tab_T[0] : 1.0;
+      if (r->nt <= 0) { V = 1.0; Vd = 0.0; }
+      set_state_TRY(r, y[0], r->rho_init * (V0 / V), y + 1); dY = ydot + 1;
+      vdv = Vd / V;
+      break;
+    }
     default: return -1;
   }
   update_rop(r);
@@ -289,7 +303,7 @@ int or_rhs(oreactor* r, double t, const double* y, double* ydot) {
     for (int k = 0; k < K; ++k) ip += r->energy[k] * r->wdot[k];
     double cp_mass = m->Rgas * mean_X(r, r->cp_R) / r->mmw;
     ydot[0] = (-ip / r->rho / cp_mass);
-  } else if (r->type == OR_CONST_VOL) {
+  } else if (r->type == OR_CONST_VOL || r->type == OR_TABLE_V) {
     /* ConstVol::EnergyDerivative (reactors.cpp:96-109) */
     double RT = m->Rgas * r->T, ip = 0.0;
     for (int k = 0; k < K; ++k) { r->energy[k] = RT * (r->h_RT[k] - 1.0); }
@@ -297,6 +311,7 @@ int or_rhs(oreactor* r, double t, const double* y, double* ydot) {
     double cp_mole = m->Rgas * mean_X(r, r->cp_R);
     double cv_mass = (cp_mole - m->Rgas) / r->mmw;
     ydot[0] = (-ip / r->rho / cv_mass);
+    if (r->type == OR_TABLE_V) ydot[0] -= (r->p * vdv) / r->rho / cv_mass; /* boundary work -p dV */
   }
   return 0;
 }

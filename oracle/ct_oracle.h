@@ -40,8 +40,13 @@ int om_nreactions(const omech*);
 
 /* reactor types: values 0..3 follow Apps::Reactor::Type
  * (/root/reference/include/applications/reactors/base.hpp:21-27); 4 is the
- * prescribed T(t),p(t) table reactor of BASELINE config 4. */
-enum { OR_CONST_PRES = 0, OR_CONST_VOL = 1, OR_CONST_TEMP_PRES = 2, OR_CONST_TEMP_VOL = 3, OR_TABLE_TP = 4 };
+ * prescribed T(t),p(t) table reactor of BASELINE config 4; 5 is the adiabatic
+ * reactor with prescribed volume V(t) and dV/dt that the reference plans next to
+ * it (README.md:18-20; no reference implementation exists: the equations are the
+ * closed-system energy balance  rho = rho0 V(t0)/V(t),  dT/dt = (-sum u_k wdot_k
+ * - p Vdot/V) / (rho cv), i.e. ConstVol::EnergyDerivative, reactors.cpp:96-109,
+ * plus the boundary work; for OR_TABLE_V the two table columns hold V and dV/dt). */
+enum { OR_CONST_PRES = 0, OR_CONST_VOL = 1, OR_CONST_TEMP_PRES = 2, OR_CONST_TEMP_VOL = 3, OR_TABLE_TP = 4, OR_TABLE_V = 5 };
 
 typedef struct oreactor oreactor;
 /* T,p,Y as in Apps::Reactor::Create (factory.hpp:15-24). */

@@ -31,7 +31,7 @@ CONSTANT_SETS = {
 }
 DEFAULT_CONSTANTS = "cantera-2.6"
 
-REACTOR_TYPES = {"Const_Pres": 0, "Const_Vol": 1, "Const_Temp_Pres": 2, "Const_Temp_Vol": 3, "Table_TP": 4}
+REACTOR_TYPES = {"Const_Pres": 0, "Const_Vol": 1, "Const_Temp_Pres": 2, "Const_Temp_Vol": 3, "Table_TP": 4, "Table_V": 5}
 
 
 def build(force=False):
@@ -254,7 +254,7 @@ class Mechanism:
         rtype = REACTOR_TYPES.get(rtype, rtype)
         T0, p0, Y0 = _f64(np.atleast_1d(T0)), _f64(np.atleast_1d(p0)), _f64(np.atleast_2d(Y0))
         n = T0.shape[0]
-        N = self.K + 1 if rtype <= 1 else self.K
+        N = self.K + 1 if rtype in (0, 1, 5) else self.K
         state = np.zeros((n, N)); tau = np.zeros(n); stats = np.zeros((n, 8), dtype=np.int64); status = np.zeros(n, dtype=np.int32)
         traj = np.zeros((n, n_out, N)) if n_out else None
         nt, tt, tT, tp = 0, None, None, None

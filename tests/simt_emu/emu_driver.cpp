@@ -87,7 +87,7 @@ static void run_init(EmuMech* m, int rt, long long n, const double* T0, const do
 int emu_rhs(void* mv, int rt, long long n, const double* T0, const double* p0, const double* Y0, const double* states,
             double* ydot, double* wdot, double* qf, double* qr) {
   EmuMech* m = (EmuMech*)mv;
-  const int N = rt <= 1 ? m->C.K + 1 : m->C.K;
+  const int N = rt_has_energy(rt) ? m->C.K + 1 : m->C.K;
   std::vector<double> st0((size_t)n * N), rho0(n);
   run_init(m, rt, n, T0, p0, Y0, st0.data(), rho0.data(), N);
   BatchArgs a{};
@@ -103,7 +103,7 @@ int emu_rhs(void* mv, int rt, long long n, const double* T0, const double* p0, c
 int emu_jacobian(void* mv, int rt, int mode, long long n, const double* T0, const double* p0, const double* Y0,
                  const double* states, double* J) {
   EmuMech* m = (EmuMech*)mv;
-  const int N = rt <= 1 ? m->C.K + 1 : m->C.K;
+  const int N = rt_has_energy(rt) ? m->C.K + 1 : m->C.K;
   std::vector<double> st0((size_t)n * N), rho0(n), scratch(warp_scratch_doubles(N, m->d.R));
   run_init(m, rt, n, T0, p0, Y0, st0.data(), rho0.data(), N);
   BatchArgs a{};
@@ -127,7 +127,7 @@ int emu_integrate(void* mv, int rt, long long n, const double* T0, const double*
                   double* traj, double* state, double* tau, long long* stats, int* status, int warps, int linsol, double jac_clip, int pool_n,
                   int slice_steps, const double* opts /* 8 or null: h_init h_min h_max nls_coef max_nef max_cor max_ncf max_order */) {
   EmuMech* m = (EmuMech*)mv;
-  const int N = rt <= 1 ? m->C.K + 1 : m->C.K;
+  const int N = rt_has_energy(rt) ? m->C.K + 1 : m->C.K;
   std::vector<double> rho0(n), tcur(n);
   run_init(m, rt, n, T0, p0, Y0, state, rho0.data(), N);
   if (warps < 1) warps = 1;

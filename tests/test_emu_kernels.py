@@ -62,9 +62,9 @@ OPTION_KEYS = ("init_step", "min_step", "max_step", "nonlin_conv_coef", "max_err
 
 
 def _integrate(emu, h, om, rt, T0, p0, Y, rtol, atol, t_end, jac=1, linsol=0, n_out=0, n_calls=1, warps=1, mxstep=20000,
-               ign=(1, 400.0), pool_n=0, slice_steps=0, options=None):
+               ign=(1, 400.0), pool_n=0, slice_steps=0, options=None, table=None):
     n = len(T0)
-    N = om.K + 1 if rt <= 1 else om.K
+    N = om.K + 1 if rt in (0, 1, 5) else om.K
     T0 = np.ascontiguousarray(T0, dtype=float); p0 = np.ascontiguousarray(p0, dtype=float); Y = np.ascontiguousarray(Y, dtype=float)
     nt = max(n_out, n_calls if n_calls > 1 else 0)
     traj = np.zeros((n, nt, N)) if nt else None
@@ -72,7 +72,11 @@ def _integrate(emu, h, om, rt, T0, p0, Y, rtol, atol, t_end, jac=1, linsol=0, n_
     opts = None
     if options:
         opts = np.array([options.get(k, 0.0) for k in OPTION_KEYS], dtype=float)
-    emu.emu_integrate(h, rt, n, P(T0), P(p0), P(Y), rtol, atol, t_end, mxstep, jac, ign[0], ign[1], n_out, n_calls, 0, None, None, None,
+    tab = (0, None, None, None)
+    if table is not None:
+        tab_arrays = [np.ascontiguousarray(a, dtype=float) for a in table]
+        tab = (len(tab_arrays[0]), P(tab_arrays[0]), P(tab_arrays[1]), P(tab_arrays[2]))
+    emu.emu_integrate(h, rt, n, P(T0), P(p0), P(Y), rtol, atol, t_end, mxstep, jac, ign[0], ign[1], n_out, n_calls, tab[0], tab[1], tab[2], tab[3],
                       P(traj), P(state), P(tau), stats.ctypes.data_as(lp), status.ctypes.data_as(ip), warps, linsol, 1.0, pool_n, slice_steps, P(opts))
     return dict(state=state, tau=tau, stats=stats, status=status, traj=traj)
 
@@ -302,3 +306,36 @@ def test_solver_option_surface_vs_oracle(emu, emech, omech):
     refb = om.integrate_batch(1, T0, p0, Y, 2e-4, rtol=1e-8, atol=1e-14, max_steps=20000, options=bad)
     gotb = _integrate(emu, h, om, 1, T0, p0, Y, 1e-8, 1e-14, 2e-4, jac=0, options=bad)
     assert np.all(refb["status"] < 0) and np.array_equal(gotb["status"], refb["status"])
+
+
+def _rcm_tables(n, nt, t_end, ratio, t_c):
+    """Rapid-compression-machine style volume history: smooth compression V0 -> V0 / ratio over t_c, then held."""
+    t = np.linspace(0.0, t_end, nt)
+    x = np.clip(t / t_c, 0.0, 1.0)
+    s_ = 0.5 * (1.0 - np.cos(np.pi * x))                       # 0 -> 1, zero slope at both ends
+    ds = 0.5 * np.pi * np.sin(np.pi * x) / t_c * (t < t_c)
+    V = 1.0 - (1.0 - 1.0 / np.asarray(ratio)[:, None]) * s_[None, :]
+    dV = -(1.0 - 1.0 / np.asarray(ratio)[:, None]) * ds[None, :]
+    return t, V * 3.0e-4, dV * 3.0e-4                          # an arbitrary volume unit: only V / V(0) enters
+
+
+@pytest.mark.parametrize("jac,linsol,n", [(1, 1, 3), (0, 0, 1)])
+def test_prescribed_volume_reactor_vs_oracle(emu, emech, omech, jac, linsol, n):
+    """Type 5 (RT_TABLE_V): adiabatic reactor in a prescribed volume V(t), dV/dt (planned by the reference, README.md:18-20).
+    The kernel source against the oracle on compression-ignition cases: H2/air compressed 8-12 x in 0.3 ms, then held;
+    analytic Jacobian + inverse (its energy row leaves out the composition dependence of the work term) and the
+    reference's configuration (difference quotients + LU)."""
+    om, h = omech("gri30"), emech("gri30")
+    t_end = 8e-4
+    T0 = np.array([500.0, 450.0, 420.0])[:n]; p0 = (np.array([1.0, 1.5, 0.8]) * 101325.0)[:n]
+    Y = np.repeat(om.X_to_Y(om.composition({"H2": 2.0, "O2": 1.0, "N2": 3.76}))[None, :], n, 0)
+    table = _rcm_tables(n, 41, t_end, [8.0, 10.0, 12.0][:n], 3e-4)
+    ref = om.integrate_batch("Table_V", T0, p0, Y, t_end, rtol=1e-9, atol=1e-15, max_steps=100000, table=table)
+    assert np.all(ref["status"] >= 0) and np.isfinite(ref["tau"]).sum() >= min(n, 2)  # compression ignites them
+    r = _integrate(emu, h, om, 5, T0, p0, Y, 1e-9, 1e-15, t_end, jac=jac, linsol=linsol, mxstep=100000, table=table)
+    assert np.all(r["status"] >= 0)
+    assert np.array_equal(np.isfinite(r["tau"]), np.isfinite(ref["tau"]))
+    ign = np.isfinite(ref["tau"])
+    assert np.abs(r["tau"][ign] / ref["tau"][ign] - 1).max() < 1e-4
+    assert np.abs(r["state"][:, 0] / ref["state"][:, 0] - 1).max() < 1e-4
+    assert np.abs(r["state"][:, 1:] - ref["state"][:, 1:]).max() < 1e-6

@@ -707,3 +707,60 @@ def test_application_yaml_to_hdf5(ctb, chem, omech, tmp_path):
     res2 = app.run(str(cfg), n_outputs=100, results_dir=str(tmp_path / "out2"), devices=list(range(min(2, ctb.device_count()))))
     assert all(np.array_equal(a["mass_fractions"], b["mass_fractions"]) and a["status"] == b["status"] for a, b in zip(res, res2))
     assert open(res[0]["file"], "rb").read() == open(res2[0]["file"], "rb").read()
+
+
+def test_prescribed_volume_reactor(ctb, chem, omech, tmp_path):
+    """Type.Table_Vol (CT_TABLE_V): adiabatic closed reactor in a prescribed volume V(t) with dV/dt given, the reactor the
+    reference plans next to the T(t), p(t) one (README.md:18-20; no reference implementation: the oracle's equations are
+    anchored on physics in tests/test_oracle_golden.py).  32 rapid-compression cases (H2/air and CH4/air compressed 8-14 x in
+    0.3 ms, then held) against the oracle at matched tolerances; a constant volume reproduces Const_Vol bit for bit; the
+    same history from a FunctionP1R2-style callable; through the multi-GPU ensemble."""
+    from chemtools_b200 import sharded
+    ch, om = chem("gri30"), omech("gri30")
+    rng = np.random.default_rng(8)
+    n, nt, t_end, t_c = 32, 61, 8e-4, 3e-4
+    T0 = rng.uniform(400.0, 520.0, n); p0 = rng.uniform(0.8, 2.0, n) * 101325.0
+    Y0 = np.concatenate([_h2_air(ch, T0[:16], rng.uniform(0.6, 1.5, 16)), _ch4_air(ch, rng.uniform(0.6, 1.5, 16))])
+    ratio = rng.uniform(8.0, 14.0, n)
+    t = np.linspace(0.0, t_end, nt)
+    x = np.clip(t / t_c, 0.0, 1.0)
+    V = 2.5e-4 * (1.0 - (1.0 - 1.0 / ratio[:, None]) * 0.5 * (1.0 - np.cos(np.pi * x))[None, :])
+    dV = -2.5e-4 * (1.0 - 1.0 / ratio[:, None]) * (0.5 * np.pi * np.sin(np.pi * x) / t_c * (t < t_c))[None, :]
+    b = ctb.ReactorBatch(ctb.Type.Table_Vol, ch, T0, p0, Y0, 1e-9, 1e-15, t_end, max_num_steps=200000)
+    assert b.n_state == ch.n_species + 1
+    assert b.Integrate(t_end) == -22                             # CT_ILL_INPUT: no table yet
+    with pytest.raises(ctb.reactors.CtError):
+        b.SetVolumeTable(t, -V, dV)                              # volumes must be positive
+    with pytest.raises(ctb.reactors.CtError):
+        b.SetTable(t, V, dV)                                     # the T-p table belongs to the other table reactor
+    b.SetVolumeTable(t, V, dV)
+    assert b.Integrate(t_end) >= 0
+    ref = om.integrate_batch("Table_V", T0, p0, Y0, t_end, rtol=1e-9, atol=1e-15, max_steps=200000, nthreads=8, table=(t, V, dV))
+    assert np.all(ref["status"] >= 0)
+    tau, tauo = b.IgnitionDelay(), ref["tau"]
+    ign = np.isfinite(tauo)
+    assert ign.sum() >= 8 and np.array_equal(np.isfinite(tau), ign)
+    assert np.abs(tau[ign] / tauo[ign] - 1).max() < TRAJ_TOL
+    settled = ~ign | (np.abs(tauo - t_end) > 0.02 * t_end)
+    assert np.abs(b.Temperature()[settled] / ref["state"][settled, 0] - 1).max() < TRAJ_TOL
+    assert np.abs(b.MassFractions()[settled] - ref["state"][settled, 1:]).max() < 1e-6
+    assert b.Temperature().min() > 700.0                          # every case was heated by the compression
+    # constant volume = the Const_Vol reactor, bit for bit
+    c = ctb.ReactorBatch(ctb.Type.Table_Vol, ch, T0[:8] + 700.0, p0[:8], Y0[:8], 1e-8, 1e-14, 2e-4, max_num_steps=50000)
+    c.SetVolumeTable(np.array([0.0, 2e-4]), np.ones((8, 2)), np.zeros((8, 2)))
+    d = ctb.ReactorBatch(ctb.Type.Const_Vol, ch, T0[:8] + 700.0, p0[:8], Y0[:8], 1e-8, 1e-14, 2e-4, max_num_steps=50000)
+    assert c.Integrate(2e-4) >= 0 and d.Integrate(2e-4) >= 0
+    assert np.array_equal(c.Solution(), d.Solution()) and np.array_equal(c.Statistics(), d.Statistics())
+    # the same history from a callable (FunctionP1R2: one parameter in, two values out), sampled into the table
+    f = ctb.ReactorBatch(ctb.Type.Table_Vol, ch, T0, p0, Y0, 1e-9, 1e-15, t_end, max_num_steps=200000)
+
+    def volume(tq):
+        xq = min(tq / t_c, 1.0)
+        return (2.5e-4 * (1.0 - (1.0 - 1.0 / ratio) * 0.5 * (1.0 - np.cos(np.pi * xq))),
+                -2.5e-4 * (1.0 - 1.0 / ratio) * (0.5 * np.pi * np.sin(np.pi * xq) / t_c if tq < t_c else 0.0))
+    f.SetTableFromFunction(volume, n_points=nt)
+    assert f.Integrate(t_end) >= 0 and np.abs(f.Temperature() / b.Temperature() - 1).max() < 1e-9
+    # and through the ensemble driver (chunks, cyclic partition): the single batch's bits
+    res = sharded.integrate(ch, ctb.Type.Table_Vol, T0, p0, Y0, 1e-9, 1e-15, t_end, devices=list(range(min(2, ctb.device_count()))),
+                            max_num_steps=200000, partition="cyclic", chunk=10, retry=False, table=(t, V, dV))
+    assert np.array_equal(res["state"], b.Solution()) and np.array_equal(res["tau"], tau, equal_nan=True)

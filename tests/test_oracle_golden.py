@@ -182,3 +182,41 @@ def test_config5_fixture_is_the_oracle(omech, config5_golden):
     for tag in ("ref", "head"):
         assert np.abs(g["tau_" + tag][ign & ok] / g["tau_tight"][ign & ok] - 1).max() < 1e-6
         assert np.abs(g["state_" + tag][ok, 0] / g["state_tight"][ok, 0] - 1).max() < 1e-6
+
+
+def test_prescribed_volume_reactor_physics(oracle, omech):
+    """OR_TABLE_V has no reference implementation to compare with (the reference only plans it, README.md:18-20), so the
+    oracle's equations are anchored on physics: (i) a constant volume reproduces the ConstVol reactor bit for bit;
+    (ii) an inert mixture compressed 10 x follows dT/dt = -(R T / W) (Vdot / V) / cv(T), integrated independently by
+    scipy with the oracle's own NASA-7 cv(T): T(t_end) to 1e-7, i.e. the isentrope with variable heat capacity;
+    (iii) the mass in the volume is conserved: rho V = const."""
+    from scipy.integrate import solve_ivp
+    om = omech("gri30")
+    Y = om.X_to_Y(om.composition({"H2": 2.0, "O2": 1.0, "N2": 3.76}))[None, :].repeat(2, 0)
+    T0 = np.array([1100.0, 1200.0]); p0 = np.full(2, 101325.0)
+    tt = np.linspace(0, 1e-3, 11)
+    a = om.integrate_batch("Const_Vol", T0, p0, Y, 1e-3, rtol=1e-9, atol=1e-15)
+    b = om.integrate_batch("Table_V", T0, p0, Y, 1e-3, rtol=1e-9, atol=1e-15, table=(tt, np.ones((2, 11)), np.zeros((2, 11))))
+    assert np.array_equal(a["state"], b["state"]) and np.array_equal(a["tau"], b["tau"]) and np.array_equal(a["stats"], b["stats"])
+    # inert compression: N2 / AR only (no reaction of GRI-3.0 has only these as reactants at 300-800 K on this time scale)
+    Yi = om.X_to_Y(om.composition({"N2": 0.79, "AR": 0.21}))[None, :]
+    t_end, ratio = 1e-3, 10.0
+    t = np.linspace(0, t_end, 201)
+    V = 1.0 - (1.0 - 1.0 / ratio) * t / t_end                      # linear in time, exactly representable by the table
+    dV = np.full_like(t, -(1.0 - 1.0 / ratio) / t_end)
+    r = om.integrate_batch("Table_V", [300.0], [101325.0], Yi, t_end, rtol=1e-10, atol=1e-16, max_steps=100000, table=(t, V[None, :], dV[None, :]))
+    assert r["status"][0] >= 0
+    X = om.Y_to_X(Yi[0]); Wm = float((X * om.W).sum())
+
+    def cv_mass(T):
+        cp_R, _, _ = om.species_thermo(float(T))
+        return om.R * (float((X * cp_R).sum()) - 1.0) / Wm
+
+    def rhs(tq, y):
+        Vq = 1.0 - (1.0 - 1.0 / ratio) * tq / t_end
+        return [-(om.R * y[0] / Wm) * (dV[0] / Vq) / cv_mass(y[0])]
+    sol = solve_ivp(rhs, (0.0, t_end), [300.0], method="DOP853", rtol=1e-12, atol=1e-12)
+    T_iso = sol.y[0, -1]
+    assert 650.0 < T_iso < 800.0                                      # ~ 300 * 10^(gamma - 1)
+    assert abs(r["state"][0, 0] / T_iso - 1) < 1e-7
+    assert np.abs(r["state"][0, 1:] - Yi[0]).max() < 1e-12           # nothing reacts
